@@ -1,0 +1,186 @@
+/*
+ * sml_b200.h -- C ABI of libsml_b200.so: hand-written sm_100a CUDA kernels for the
+ * per-period retraining hot path of SML (reference: zyang1580/SML, a pure-Python /
+ * PyTorch program with no FFI layer of its own -- SURVEY.md section 8b).
+ *
+ * The reference has no plugin interface; the drop-in boundary is its Python class
+ * surface (sml_b200/model/*.py mirrors it).  These entry points are what those
+ * classes bind through ctypes, one per stock-PyTorch op sequence they replace; the
+ * reference lines each one replaces are cited as (file:line under /root/reference).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - the library never allocates or frees persistent memory: callers own all
+ *     tensors and pass a scratch workspace (size from sml_*_workspace_bytes);
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*), do not
+ *     synchronise, and are CUDA-graph capturable;
+ *   - return 0 on success, a negative SML_E_* code otherwise; the message is in
+ *     sml_last_error() (thread-local);
+ *   - latent dimension d must be 64 (the reference default, main_yelp.py:41); other
+ *     values return SML_E_UNSUPPORTED;
+ *   - there is no CPU path: every entry point fails with SML_E_ARCH on a device
+ *     that is not compute capability 10.x.
+ */
+#ifndef SML_B200_H
+#define SML_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SML_ABI_VERSION 1
+
+#define SML_OK 0
+#define SML_E_BADARG (-1)
+#define SML_E_ARCH (-2)
+#define SML_E_CUDA (-3)
+#define SML_E_UNSUPPORTED (-4)
+#define SML_E_WORKSPACE (-5)
+
+#define SML_D 64 /* latent dim */
+
+/* ---- theta layout --------------------------------------------------------------
+ * One transfer net (one_transfer, model/conv_transfer.py:18-50) is a flat fp32 block of
+ * SML_NET_STRIDE floats; segments are padded so that every segment starts 128-byte
+ * aligned (padding stays zero).  A ConvTransfer(_com) module (model/conv_transfer.py:
+ * 52-56, 87-91) is [user net | item net] = 2 * SML_NET_STRIDE floats.  The Python
+ * nn.Parameters are views into this block with the reference's shapes/state_dict keys.
+ *   conv1.weight (10,1,R,1) at +0      (R = 3 for ConvTransfer_com, 2 for ConvTransfer)
+ *   conv1.bias   (10)       at +32
+ *   conv2.weight (5,10,1,1) at +64
+ *   conv2.bias   (5)        at +128
+ *   fc1.weight   (512,320)  at +160
+ *   fc1.bias     (512)      at +164000
+ *   fc2.weight   (64,512)   at +164512
+ *   fc2.bias     (64)       at +197280
+ */
+#define SML_OFF_C1W 0
+#define SML_OFF_C1B 32
+#define SML_OFF_C2W 64
+#define SML_OFF_C2B 128
+#define SML_OFF_F1W 160
+#define SML_OFF_F1B 164000
+#define SML_OFF_F2W 164512
+#define SML_OFF_F2B 197280
+#define SML_NET_STRIDE 197344
+#define SML_FC1_OUT 512
+#define SML_FC1_IN 320
+
+/* transfer variants */
+#define SML_VARIANT_COM 3  /* ConvTransfer_com: rows [x_t, x_hat, x_t*x_hat/||x_t||]  (conv_transfer.py:92-110) */
+#define SML_VARIANT_CONV 2 /* ConvTransfer: rows [x_t, x_hat], user output / ||.||     (conv_transfer.py:57-69)  */
+/* loss kinds (ConvTransfer_com.run_MF, conv_transfer.py:122-134) */
+#define SML_LOSS_BCE 0
+#define SML_LOSS_BPR 1
+
+int sml_abi_version(void);
+const char *sml_last_error(void);
+/* 0 if the current device is sm_100-class, SML_E_ARCH otherwise. */
+int sml_device_check(void);
+/* Number of SMs on the current device (grid sizing in the host code). */
+int sml_sm_count(void);
+
+/* ---- candidate-list evaluation ---------------------------------------------------
+ * Replaces MFbasemode.test (model/MF.py:45-80): rows[n, 0] = user id, rows[n, 1..C] =
+ * candidate item ids, candidate 0 is the positive.  For every test row writes
+ *   gt[n] = #{j>0 : s_j > s_0}, eq[n] = #{j>0 : s_j == s_0}   (NaN sorts highest)
+ * with s_j = <user_tab[u], item_tab[c_j]> in fp32.  The position of the positive in
+ * torch.topk's output is gt (+eq: the reference's tie order).
+ * row_stride = number of int64 per row (>= 1 + C). */
+int sml_eval_candidates(const float *user_tab, const float *item_tab, int d, const int64_t *rows, int64_t n_rows,
+                        int64_t row_stride, int n_cand, int32_t *gt, int32_t *eq, void *stream);
+/* Per batch of `batch` consecutive test rows (evaluation2.test_model batches of 1024,
+ * evalution/evaluation2.py:8-26): hits[b] = #{rank < topk}, ndcg[b] = sum 1/log2(rank+2)
+ * over hits (fp32, fixed summation order), rank = gt + (tie_loses ? eq : 0). */
+int sml_eval_reduce(const int32_t *gt, const int32_t *eq, int64_t n_rows, int batch, int topk, int tie_loses,
+                    int32_t *hits, float *ndcg, void *stream);
+/* Scores for (user, item) id pairs: MFbasemode.forward (model/MF.py:34-43).
+ * score[n] = <user_tab[user[n]], item_tab[item[n]]>; if norm != 0 divided by ||user row||. */
+int sml_pair_scores(const float *user_tab, const float *item_tab, int d, const int64_t *user, const int64_t *item,
+                    int64_t n, int norm, float *score, void *stream);
+
+/* ---- transfer forward -------------------------------------------------------------
+ * Replaces ConvTransfer_com.forward / ConvTransfer.forward (model/conv_transfer.py:57-69,
+ * 92-110) and therefore meta_train.updata (model/transfer.py:884-902):
+ *   out[n] = one_transfer_theta(stack(x_t[i_n], x_hat[i_n]))   i_n = ids ? ids[n] : n
+ * theta_net points at ONE net (user or item).  normalize_out != 0 divides each output row
+ * by its L2 norm (ConvTransfer 'user' type).  out may not alias x_t / x_hat. */
+size_t sml_transfer_fwd_workspace_bytes(int64_t n_rows);
+int sml_transfer_fwd(const float *x_t, const float *x_hat, const int64_t *ids, int64_t n_rows, int d, int variant,
+                     const float *theta_net, int normalize_out, float *out, void *workspace, size_t workspace_bytes,
+                     void *stream);
+
+/* ---- optimizer scalars ------------------------------------------------------------
+ * torch.optim.Adam keeps one step counter per parameter and derives step_size and
+ * sqrt(bias_correction2) from it on the host (model/transfer.py:392-393).  To stay
+ * graph-capturable the counter lives on the device: sml_adam_tick increments
+ * state[0] (int64) and writes step_size = lr/(1-b1^t) and sqrt(1-b2^t) as floats at
+ * state[1], state[2] (computed in double). `state` = 4 int64 slots. */
+int sml_adam_tick(int64_t *state, double lr, double beta1, double beta2, void *stream);
+/* Dense Adam over n floats (torch defaults eps=1e-8, amsgrad off; coupled L2 weight_decay):
+ *   g' = g + wd*p; m += (g'-m)*(1-b1); v = b2*v + (1-b2)*g'^2; p -= step_size*m/(sqrt(v)/sqrt(bc2)+eps)
+ * If zero_grad != 0 the gradient buffer is zeroed after use (replaces zero_grad(),
+ * model/transfer.py:464-465,702). */
+int sml_adam_dense(float *p, float *m, float *v, float *g, int64_t n, const int64_t *state, double beta1, double beta2,
+                   double eps, double weight_decay, int zero_grad, void *stream);
+
+/* ---- SML steps ----------------------------------------------------------------------
+ * Shared argument block for the two hot loops.  Rows [0,B) of every workspace matrix are
+ * the user rows (user net), [B,2B) the positive-item rows and [2B,3B) the negative-item
+ * rows (item net). */
+typedef struct {
+    /* batch */
+    const int64_t *user, *item, *neg; /* [B] ids */
+    int64_t batch;
+    /* tables, [n_users|n_items, 64] fp32 row-major */
+    const float *last_user, *last_item; /* w_{t-1}: x_t source (never written)                     */
+    float *hat_user, *hat_item;         /* x_hat source. MF step: the live MFbase latent tables      */
+                                        /* (updated in place); TR step: the w_hat snapshots (read)   */
+    int64_t n_users, n_items;
+    /* transfer parameters: [user net | item net] */
+    float *theta;
+    int variant; /* SML_VARIANT_* */
+    int loss;    /* SML_LOSS_*    */
+    /* MF step only: dense gradient scratch (all-zero on entry and on exit) + Adam state */
+    float *g_user, *g_item, *m_user, *v_user, *m_item, *v_item;
+    int64_t *adam_state; /* 4 x int64, see sml_adam_tick */
+    double lr, l2;       /* MF: MF_lr, l2 (model/transfer.py:486-488); TR: TR_lr, TR_l2 (weight decay) */
+    /* TR step only: theta gradient + Adam state, each 2*SML_NET_STRIDE floats */
+    float *g_theta, *m_theta, *v_theta;
+    /* outputs */
+    float *loss_out; /* [2]: loss_out[0] = this step's loss (as the reference's loss_batch),      */
+                     /*      loss_out[1] += loss (the reference's loss_all accumulation, :501,722) */
+    /* scratch */
+    void *workspace;
+    size_t workspace_bytes;
+} sml_step_args;
+
+size_t sml_step_workspace_bytes(int64_t batch);
+/* HOT LOOP A body, model/transfer.py:463-511: gather -> transfer fwd (3 nets calls) -> BCE
+ * -> + l2*0.5*sum(w_hat^2) -> row gradients through the x_hat channel -> scatter-add ->
+ * dense Adam on both latent tables.  theta is read-only here. */
+int sml_mf_step(const sml_step_args *args, void *stream);
+/* HOT LOOP B body, model/transfer.py:701-728: same forward on snapshot rows, theta
+ * gradients only, Adam with coupled L2 on theta. */
+int sml_tr_step(const sml_step_args *args, void *stream);
+/* Forward + loss + gradients without any optimizer update (ConvTransfer_com.run_MF +
+ * backward, model/conv_transfer.py:113-135): writes d_rows [3B,64] = dL/d x_hat rows (no l2
+ * term) if non-null and accumulates theta gradients into args->g_theta if non-null. */
+int sml_run_mf_grads(const sml_step_args *args, float *d_rows, float *scores /* [2B] s+, s- or null */, void *stream);
+
+/* ---- plain MF steps (baselines / MF2; north_star kernel 1) ---------------------------
+ * model/baseline.py:188-201 (BCE, mean, separate l2_u / l2_i) and MF2.forward
+ * (model/MF.py:129-147, BPR sum with item biases): fused gather - dot - loss - scatter-add
+ * into the dense gradient buffers, then sml_adam_dense by the caller.  bias pointers may be
+ * null (BCE path ignores them). */
+int sml_plain_mf_grads(const float *user_tab, const float *item_tab, const float *item_bias, const int64_t *user,
+                       const int64_t *item, const int64_t *neg, int64_t batch, int d, int loss, double l2_u,
+                       double l2_i, float *g_user, float *g_item, float *g_item_bias, float *loss_out,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SML_B200_H */

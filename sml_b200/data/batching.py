@@ -1,0 +1,93 @@
+"""Host-side batch construction for the two hot loops.
+
+The reference feeds its loops from ``torch.utils.data.DataLoader(shuffle=True)`` over per-sample
+Python ``__getitem__`` calls (model/transfer.py:438-443,692-696).  Here a whole epoch is
+materialised at once as three int64 arrays (user, item, neg) in batch order, uploaded once, and
+the step kernels walk it on the device.
+
+``ReferenceStream`` reproduces, draw for draw, what the reference consumes from the *global* torch
+and numpy generators with ``--numworkers 0``, so that a run seeded like main_yelp.py:137-140 sees
+bit-identical triples ("sampled indices bit-exact", BASELINE.json north_star):
+  * every DataLoader iterator draws one int64 ``_base_seed`` from the global torch generator,
+    also the un-shuffled evaluation loaders (torch/utils/data/dataloader.py, _BaseDataLoaderIter);
+  * a shuffled loader then draws the RandomSampler seed and permutes with a private generator;
+  * trainDataset_withPreSample shuffles its column list with ``np.random.shuffle``;
+  * offlineDataset_withsample calls ``np.random.choice(item_all, 1)`` once per sample (and once per
+    rejection) in sampler order.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .dataset import offlineDataset_withsample
+from .dataset2 import trainDataset_withPreSample
+
+
+class ReferenceStream(object):
+    """Mirrors the reference's consumption of the global RNGs (see module docstring)."""
+
+    @staticmethod
+    def loader_iter():
+        """One DataLoader iterator creation (train or eval)."""
+        torch.empty((), dtype=torch.int64).random_()
+
+    @staticmethod
+    def shuffled_order(n):
+        ReferenceStream.loader_iter()
+        seed = int(torch.empty((), dtype=torch.int64).random_().item())
+        g = torch.Generator()
+        g.manual_seed(seed)
+        return torch.randperm(n, generator=g).numpy()
+
+    @staticmethod
+    def alone_negatives(ds: offlineDataset_withsample, order):
+        """Sequential rejection sampling in sampler order, vectorised between rejections."""
+        n = len(order)
+        users = ds.user[order]
+        P = len(ds.item_all)
+        state = np.random.get_state()
+        margin = max(64, n // 8)
+        while True:
+            draws = np.random.randint(0, P, size=n + margin)
+            neg = np.empty(n, dtype=ds.item_all.dtype)
+            s = 0          # next sample
+            p = 0          # next draw
+            ok = True
+            while s < n:
+                m = min(n - s, len(draws) - p)
+                if m <= 0:
+                    ok = False
+                    break
+                cand = ds.item_all[draws[p:p + m]]
+                rej = ds.interacted(users[s:s + m], cand)
+                k = int(np.argmax(rej)) if rej.any() else m
+                neg[s:s + k] = cand[:k]
+                s += k
+                p += k
+                if k < m:
+                    p += 1        # the rejected draw is consumed; sample s retries with the next draw
+            if ok:
+                break
+            np.random.set_state(state)
+            margin *= 2
+        # leave the global generator exactly where the reference would: p draws consumed
+        np.random.set_state(state)
+        if p:
+            np.random.randint(0, P, size=p)
+        return neg
+
+
+def mf_epoch_triples(ds: trainDataset_withPreSample, order):
+    """One MF epoch over a pre-sampled dataset in the given sample order (data/dataset2.py:191-201)."""
+    col = ds.current_column()
+    d = ds.all_data
+    u, i, j = d[order, 0], d[order, 1], d[order, col]
+    ds.advance_epoch()
+    return np.ascontiguousarray(u, dtype=np.int64), np.ascontiguousarray(i, dtype=np.int64), np.ascontiguousarray(j, dtype=np.int64)
+
+
+def tr_epoch_triples(ds: offlineDataset_withsample, order):
+    neg = ReferenceStream.alone_negatives(ds, order)
+    return (np.ascontiguousarray(ds.user[order], dtype=np.int64), np.ascontiguousarray(ds.item[order], dtype=np.int64),
+            np.ascontiguousarray(neg, dtype=np.int64))

@@ -1,0 +1,498 @@
+"""SML period orchestrator -- drop-in for ``meta_train`` of the reference's model/transfer.py:302-1031.
+
+Same constructor, methods and attributes as the reference (``MFbase``, ``transfer``,
+``last_user_weight`` ... ``MF_optimizer``, ``transfer_optimizer``, ``recall``/``ndcg`` lists), same
+period state machine and the same quirks (SURVEY.md section 7 hard part 4), but every device
+operation of the two hot loops, ``updata()`` and the evaluation is a kernel of libsml_b200.so:
+
+  reference (stock PyTorch)                              here
+  -----------------------------------------------------  ------------------------------------------
+  DataLoader + per-sample __getitem__ (:438-443)         whole epoch of (u,i,j) uploaded once
+  6 gathers + run_MF + backward + dense Adam (:463-511)  ops.mf_step   (sml_mf_step)
+  6 gathers + run_MF + backward + Adam(theta) (:701-728) ops.tr_step   (sml_tr_step)
+  transfer(all rows) + copy_ (:884-902)                  ops.transfer_forward straight into MFbase
+  test_model over 1024-row batches (:445,518,685,740)    one fused gather-dot-rank launch per set
+
+There is no CPU / eager-PyTorch fallback: without the CUDA library every step raises.
+"""
+from __future__ import annotations
+
+import copy
+import io
+import pickle
+import time
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..data.batching import ReferenceStream, mf_epoch_triples, tr_epoch_triples
+from ..data.dataset import offlineDataset_withsample as SampleDaset
+from ..data.dataset2 import trainDataset_withPreSample as PreSampleDatast
+from ..data.dataset2 import transfer_data  # noqa: F401  (re-exported like the reference)
+from ..evalution.evaluation2 import DeviceTestSet, test_model
+from . import MF
+from .conv_transfer import ConvTransfer, ConvTransfer_com
+
+
+class FusedAdam(object):
+    """The slice of torch.optim.Adam's interface the reference touches (``param_groups``, ``state``,
+    ``zero_grad``, ``state_dict``), backed by the fused kernels: the update itself happens inside
+    sml_mf_step / sml_tr_step, which read ``param_groups[0]['lr'|'weight_decay']`` every step."""
+
+    def __init__(self, params, lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8):
+        self.param_groups = [dict(params=list(params), lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                                  amsgrad=False)]
+        self.state = {}
+        self.adam_state = None        # device int64[4]: step counter + packed step scalars
+
+    @property
+    def step_count(self):
+        return 0 if self.adam_state is None else int(self.adam_state[0].item())
+
+    def zero_grad(self, set_to_none=True):
+        pass                          # gradients are re-zeroed by the fused update
+
+    def step(self):
+        raise RuntimeError("FusedAdam.step() is fused into ops.mf_step / ops.tr_step")
+
+    def state_dict(self):
+        return dict(step=self.step_count, param_groups=[{k: v for k, v in g.items() if k != "params"} for g in self.param_groups],
+                    state={k: {n: t.detach().clone() for n, t in v.items()} for k, v in self.state.items()})
+
+
+class _RemapUnpickler(pickle.Unpickler):
+    """``torch.load(args.pre_model)`` in the reference unpickles a whole ``model.MF.MFbasemode``
+    (model/transfer.py:322-325); map that module path onto this package."""
+
+    def find_class(self, module, name):
+        if module in ("model.MF", "MF"):
+            module = "sml_b200.model.MF"
+        return super().find_class(module, name)
+
+
+class _RemapPickle(object):
+    Unpickler = _RemapUnpickler
+    __name__ = "sml_b200_remap_pickle"
+
+    @staticmethod
+    def load(f, **kw):
+        return _RemapUnpickler(f, **kw).load()
+
+
+def load_pre_model(path, user_num, item_num, laten_dim, device):
+    """Pickled module (reference format), an MFbasemode of this package, or a plain state_dict."""
+    obj = torch.load(path, map_location="cpu", weights_only=False, pickle_module=_RemapPickle)
+    if isinstance(obj, dict):
+        with torch.random.fork_rng(devices=[]):     # do not disturb the global generator (batch-order parity)
+            m = MF.MFbasemode(num_user=user_num, num_item=item_num, laten_factor=laten_dim)
+        m.load_state_dict(obj)
+        obj = m
+    return obj.to(device)
+
+
+class meta_train(object):
+    """SML model (reference: model/transfer.py:302-1031)."""
+
+    def __init__(self, args, datasets, user_num, item_num, laten_dim, device=None, batch_source=None,
+                 emulate_reference_rng=True):
+        """``batch_source``: optional callable (kind, stage_id, epoch, n_rows) -> (user, item, neg) int64
+        numpy arrays in batch order; when given it supplies the triples of every epoch (north_star:
+        "the same supplied negative-sample indices").  Otherwise triples are drawn like the reference
+        does (``emulate_reference_rng``: same global-RNG consumption as ``--numworkers 0``)."""
+        self._require_device(device)
+        user_num, item_num = int(user_num), int(item_num)
+        if laten_dim != 64:
+            raise ValueError("sml_b200 kernels are specialised for laten=64 (the reference default)")
+        if getattr(args, "TR_with_MF_bias", False):
+            raise NotImplementedError("TR_with_MF_bias (65-wide transfer input) is not supported; reference default is False")
+        if getattr(args, "clip_grad", False) or getattr(args, "need_adaptive", False) or getattr(args, "norm", False):
+            raise NotImplementedError("clip_grad / need_adaptive / norm are off in the reference's final version "
+                                      "(main_yelp.py:50-55,104) and are not implemented")
+        self.batch_source = batch_source
+        self.emulate_reference_rng = emulate_reference_rng
+        self.MFbase = load_pre_model(args.pre_model, user_num, item_num, laten_dim, self.device)
+
+        self.transfer_type = args.transfer_type
+        self.with_MF_bias = False
+        self.test_in_TR_train = args.test_in_TR_Train
+        self.TR_train_sampleTYpe = args.TR_sample_type
+        print("with MF bias:", self.with_MF_bias)
+        print("transfer type:", self.transfer_type)
+        self.need_writer = args.need_writer
+        self.MF_TrainDataset = None
+        if args.MF_sample == "alone":
+            self.MF_TrainDataset = SampleDaset
+        elif args.MF_sample == "all":
+            self.MF_TrainDataset = PreSampleDatast
+        if args.need_writer:
+            from torch.utils.tensorboard import SummaryWriter
+            path = ("m-num" + str(args.multi_num) + "-MF-lr" + str(args.MF_lr) + "-l2-" + str(args.l2) + "e-" + str(args.MF_epochs)
+                    + "--TR-lr" + str(args.TR_lr) + "-l2-" + str(args.TR_l2) + "-e-" + str(args.TR_epochs)
+                    + str(args.TR_sample_type) + "user-norm" + str(args.norm))
+            self.writer = SummaryWriter(comment=path)
+
+        uw, iw = self.MFbase.user_laten.weight.data, self.MFbase.item_laten.weight.data
+        input_dim = laten_dim
+        self.last_user_weight = torch.zeros_like(uw)                  # model/transfer.py:358-364
+        self.last_item_weight = torch.zeros_like(iw)
+        self.user_weight_hat = copy.deepcopy(uw)
+        self.item_weight_hat = copy.deepcopy(iw)
+        self.last_user_weight_hat = copy.deepcopy(self.user_weight_hat)
+        self.last_item_weight_hat = copy.deepcopy(self.item_weight_hat)
+
+        if self.transfer_type == "conv":
+            self.transfer = ConvTransfer(input_dim, input_dim).to(self.device)
+            self.transfer_type = "transfer2"
+        elif self.transfer_type == "conv_com":
+            self.transfer = ConvTransfer_com(input_dim, input_dim).to(self.device)
+            self.transfer_type = "transfer2"
+        elif self.transfer_type in ("transfer", "transfer2", "GRU", "transfer3", "conv_com2"):
+            raise NotImplementedError("transfer_type %r is one of the reference's unused alternatives "
+                                      "(model/transfer.py:1-5); only conv_com / conv are built" % self.transfer_type)
+        else:
+            raise TypeError("No such type transfer!!!")
+
+        self.dataset = datasets
+
+        self.MF_optimizer = FusedAdam(self.MFbase.parameters(), lr=args.MF_lr, weight_decay=0)
+        self.transfer_optimizer = FusedAdam(self.transfer.parameters(), lr=args.TR_lr, weight_decay=args.TR_l2)
+        z = torch.zeros_like
+        self._mf = dict(m_user=z(uw), v_user=z(uw), m_item=z(iw), v_item=z(iw), g_user=z(uw), g_item=z(iw))
+        self.MF_optimizer.adam_state = ops.new_adam_state(self.device)
+        self.MF_optimizer.state = {self.MFbase.user_laten.weight: dict(exp_avg=self._mf["m_user"], exp_avg_sq=self._mf["v_user"]),
+                                   self.MFbase.item_laten.weight: dict(exp_avg=self._mf["m_item"], exp_avg_sq=self._mf["v_item"])}
+        th = self.transfer.theta
+        self._tr = dict(m=z(th), v=z(th))
+        self.transfer_optimizer.adam_state = ops.new_adam_state(self.device)
+        self.transfer_optimizer.state = {"theta": dict(exp_avg=self._tr["m"], exp_avg_sq=self._tr["v"])}
+        self._loss = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self._ws = {}
+        self._dev_cache = {}
+
+        self.recall = []
+        self.ndcg = []
+        self.test_num = []
+        self.recall_5 = []
+        self.ndcg_5 = []
+        self.MF_itr = 0
+        self.TR_itr = 0
+        self.recall_10 = []
+        self.ndcg_10 = []
+        self.timers = dict(mf=0.0, tr=0.0, updata=0.0, eval=0.0)     # host wall-clock, only for reporting
+
+    # ------------------------------------------------------------------ helpers
+    def _require_device(self, device):
+        ops.lib()                                            # fail loudly if the CUDA library is missing
+        if not torch.cuda.is_available():
+            raise RuntimeError("sml_b200.meta_train needs a CUDA device (no CPU path)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+    def _workspace(self, B):
+        if B not in self._ws:
+            self._ws[B] = torch.zeros(int(ops.lib().sml_step_workspace_bytes(B)), dtype=torch.uint8, device=self.device)
+        return self._ws[B]
+
+    def _to_device(self, arr):
+        """numpy int array -> cached int64 device tensor (period files are re-used across stages)."""
+        key = id(arr)
+        hit = self._dev_cache.get(key)
+        if hit is not None and hit[0] is arr:
+            return hit[1]
+        t = torch.from_numpy(np.ascontiguousarray(arr)).to(self.device, dtype=torch.int64, non_blocking=False)
+        if len(self._dev_cache) > 6:
+            self._dev_cache.pop(next(iter(self._dev_cache)))
+        self._dev_cache[key] = (arr, t)
+        return t
+
+    def _test_set(self, arr):
+        return DeviceTestSet(self._to_device(arr), emulate_reference_rng=self.emulate_reference_rng)
+
+    def _triples(self, kind, ds, stage_id, epoch, n_rows):
+        if self.batch_source is not None:
+            u, i, j = self.batch_source(kind, stage_id, epoch, n_rows)
+            if isinstance(ds, PreSampleDatast):
+                ds.advance_epoch()
+        else:
+            order = ReferenceStream.shuffled_order(n_rows) if self.emulate_reference_rng else np.random.permutation(n_rows)
+            if isinstance(ds, PreSampleDatast):
+                u, i, j = mf_epoch_triples(ds, order)
+            else:
+                u, i, j = tr_epoch_triples(ds, order)
+        return u, i, j
+
+    def _upload(self, arrs):
+        return [torch.from_numpy(np.ascontiguousarray(x, dtype=np.int64)).to(self.device) for x in arrs]
+
+    def _eval(self, test_set, topK):
+        t0 = time.perf_counter()
+        r = test_model(self.MFbase, test_set, topK=topK)
+        self.timers["eval"] += time.perf_counter() - t0
+        return r
+
+    def get_next_data(self, stage_id):
+        set_t, set_tt, now_test, val = self.dataset.next_train(stage_id)
+        return set_t, set_tt, now_test, val
+
+    # ------------------------------------------------------------------ MF (inner) training
+    def MF_train_onestage(self, args, set_t, stage_id, val=None):
+        """reference: model/transfer.py:417-534 (transfer fixed, MFbase trained through it)."""
+        self.transfer.eval()
+        if val is not None:
+            val = self._test_set(val)
+        print("******MF (inner) training ******")
+        set_t_ds = self.MF_TrainDataset(set_t)
+        if val is not None:
+            recall, ndcg = self._eval(val, args.topK)
+            print("before train MF test:recall:{:.4f} ndcg:{:.4f}".format(recall, ndcg))
+            if self.need_writer:
+                self.writer.add_scalar("Acc/MF-recall" + str(args.topK), recall, self.MF_itr)
+                self.writer.add_scalar("Acc/MF-ndcg" + str(args.topK), ndcg, self.MF_itr)
+                self.writer.add_scalar("norm/user-norm", (self.MFbase.user_laten.weight.data ** 2).sum(dim=-1).mean(), self.MF_itr)
+                self.MF_itr += 1
+        for epoch in range(args.MF_epochs):
+            self.MFbase.train()
+            self.transfer.eval()
+            t0 = time.perf_counter()
+            triples = self._triples("MF", set_t_ds, stage_id, epoch, len(set_t_ds))
+            loss_all = self._mf_epoch(args, triples) / args.MF_batch_size       # :514-515
+            self.timers["mf"] += time.perf_counter() - t0
+            if val is not None:
+                recall, ndcg = self._eval(val, args.topK)
+                print("MF-stage:", stage_id, "epoch:", epoch, "loss:{:.5f}".format(loss_all), "recall:{:.4f}".format(recall),
+                      "ndcg:{:.4f}".format(ndcg))
+                if self.need_writer:
+                    self.writer.add_scalar("Acc/MF-recall" + str(args.topK), recall, self.MF_itr)
+                    self.writer.add_scalar("Acc/MF-ndcg" + str(args.topK), ndcg, self.MF_itr)
+                    self.writer.add_scalar("Loss/MF-loss", loss_all, self.MF_itr)
+            else:
+                print("MF-stage:", stage_id, "epoch:", epoch, "loss:", loss_all)
+            if self.need_writer:
+                self.writer.add_scalar("norm/user-norm", (self.MFbase.user_laten.weight.data ** 2).sum(dim=-1).mean(), self.MF_itr)
+                self.MF_itr += 1
+            self.last_MF_loss = loss_all
+
+    def _mf_epoch(self, args, triples):
+        """HOT LOOP A (model/transfer.py:463-511) over one epoch of triples; returns the mean batch loss."""
+        user, item, neg = self._upload(triples)
+        uw, iw = self.MFbase.user_laten.weight.data, self.MFbase.item_laten.weight.data
+        B = int(args.MF_batch_size)
+        ws = self._workspace(B)
+        n = user.numel()
+        self._loss.zero_()
+        nb = 0
+        lr = self.MF_optimizer.param_groups[0]["lr"]
+        for s in range(0, n, B):
+            e = min(s + B, n)
+            a = ops.make_step_args(user=user[s:e], item=item[s:e], neg=neg[s:e],
+                                   last_user=self.last_user_weight, last_item=self.last_item_weight,
+                                   hat_user=uw, hat_item=iw, theta=self.transfer.theta, variant=self.transfer.variant,
+                                   loss=ops.LOSS_BCE if self.transfer.variant == ops.VARIANT_COM else ops.LOSS_BPR,
+                                   adam_state=self.MF_optimizer.adam_state, lr=lr, l2=args.l2, loss_out=self._loss,
+                                   workspace=ws, **self._mf)
+            ops.mf_step(a)
+            nb += 1
+        return self._loss[1].item() / nb
+
+    # ------------------------------------------------------------------ transfer (outer) training
+    def transfer_train_onestage(self, args, set_tt, stage_id, compute_performance=False, val=None):
+        """reference: model/transfer.py:644-749 (embeddings fixed, theta trained)."""
+        print("********* this is Transfer model training stage ***********")
+        self.MFbase.eval()
+        now_test = None
+        if self.TR_train_sampleTYpe == "alone":
+            set_tt_ds = SampleDaset(set_tt)
+            compute_performance = False
+            if val is not None:
+                now_test = self._test_set(val)
+                compute_performance = True
+        elif self.TR_train_sampleTYpe == "all":
+            now_test = self._test_set(set_tt)
+            set_tt_ds = PreSampleDatast(set_tt)
+            compute_performance = True
+        else:
+            raise TypeError("no such TR sample type")
+        if compute_performance:
+            recall, ndcg = self._eval(now_test, args.topK)
+            print("before train transfer test:recall:{:.4f} ndcg:{:.4f}".format(recall, ndcg))
+            if self.need_writer:
+                self.writer.add_scalar("Acc/tr-TR-recall@" + str(args.topK), recall, self.TR_itr)
+                self.writer.add_scalar("Acc/tr-TR-ndcg@" + str(args.topK), ndcg, self.TR_itr)
+                self.TR_itr += 1
+        s_time = time.time()
+        for epoch in range(args.TR_epochs):
+            self.transfer.train()
+            t0 = time.perf_counter()
+            triples = self._triples("TR", set_tt_ds, stage_id, epoch, len(set_tt_ds))
+            loss_all = self._tr_epoch(args, triples)
+            self.timers["tr"] += time.perf_counter() - t0
+            print("one epcohs TR time cost:", time.time() - s_time)
+            if self.need_writer:
+                self.writer.add_scalar("Loss/TR-loss", loss_all / args.TR_batch_size, self.TR_itr)
+            if compute_performance:
+                self.updata()
+                recall, ndcg = self._eval(now_test, args.topK)
+                print("stage:{}, epcoh：{}，loss:{:.4f},*****val result  reacll:{:.4f}  ndcg:{:.4f}".format(
+                    stage_id, epoch, loss_all / args.TR_batch_size, recall, ndcg))
+                if self.need_writer:
+                    self.writer.add_scalar("Acc/tr-TR-recall@" + str(args.topK), recall, self.TR_itr)
+                    self.writer.add_scalar("Acc/tr-TR-ndcg@" + str(args.topK), ndcg, self.TR_itr)
+            else:
+                print("stage:", stage_id, "epoch:", epoch, "transfer train loss:", loss_all / args.TR_batch_size)
+            self.last_TR_loss = loss_all
+        print("stage ", stage_id, " transfer trained finished!!!!")
+
+    def _tr_epoch(self, args, triples):
+        """HOT LOOP B (model/transfer.py:701-728) over one epoch of triples; returns the mean batch loss."""
+        user, item, neg = self._upload(triples)
+        B = int(args.TR_batch_size)
+        ws = self._workspace(B)
+        n = user.numel()
+        self._loss.zero_()
+        nb = 0
+        g = self.transfer_optimizer.param_groups[0]
+        for s in range(0, n, B):
+            e = min(s + B, n)
+            a = ops.make_step_args(user=user[s:e], item=item[s:e], neg=neg[s:e],
+                                   last_user=self.last_user_weight, last_item=self.last_item_weight,
+                                   hat_user=self.user_weight_hat, hat_item=self.item_weight_hat,
+                                   theta=self.transfer.theta, variant=self.transfer.variant,
+                                   loss=ops.LOSS_BCE if self.transfer.variant == ops.VARIANT_COM else ops.LOSS_BPR,
+                                   adam_state=self.transfer_optimizer.adam_state, lr=g["lr"], l2=g["weight_decay"],
+                                   g_theta=self.transfer.theta_grad, m_theta=self._tr["m"], v_theta=self._tr["v"],
+                                   loss_out=self._loss, workspace=ws)
+            ops.tr_step(a)
+            nb += 1
+        return self._loss[1].item() / nb
+
+    # ------------------------------------------------------------------ one period
+    def _real_test(self, now_test_arr):
+        """The three test_model calls at K = 20, 10, 5 (model/transfer.py:810-823,855-868)."""
+        self.test_num.append(now_test_arr.shape[0])
+        now_test = self._test_set(now_test_arr)
+        for K, rl, nl, tag in ((20, self.recall, self.ndcg, ""), (10, self.recall_10, self.ndcg_10, " @10"),
+                               (5, self.recall_5, self.ndcg_5, " @5")):
+            recall, ndcg = self._eval(now_test, K)
+            print("test result ---------{} reacll:{:.4f}  ndcg:{:.4f}".format(tag, recall, ndcg))
+            rl.append(recall)
+            nl.append(ndcg.cpu().numpy())
+
+    def train_one_stage3(self, args, stage_id):
+        """reference: model/transfer.py:753-881 -- one period, three branches."""
+        self.save_MF_weight(save_as="last")
+        set_t, set_tt, now_test, val = self.get_next_data(stage_id)
+        if set_t is None:
+            return False
+        if now_test is None:                       # online training, no real test yet (:772-792)
+            for phase in range(args.multi_num):
+                self.MF_train_onestage(args, set_t, stage_id, val=val)
+                self.MFbase.eval()
+                self.save_MF_weight(save_as="hat")
+                self.updata()
+                self.transfer_train_onestage(args, set_tt, stage_id, val=val)
+                if args.Load_W_hat:
+                    self.load_MFbase_weight(self.user_weight_hat, self.item_weight_hat)
+            self.updata()
+            return True
+        elif set_tt is None:                       # transfer frozen while testing (:793-825)
+            s_time = time.time()
+            print("stop train transfer while test###!!!!!")
+            args.MF_epochs = 2                     # the reference mutates args here (:796)
+            self.MF_train_onestage(args, set_t, stage_id, val=val)
+            self.MFbase.eval()
+            self.save_MF_weight(save_as="hat")
+            self.updata()
+            print("only traning time cost:", time.time() - s_time)
+            self._real_test(now_test)
+            print("include test time cost:", time.time() - s_time)
+            return True
+        else:                                      # test on D_{t+1}, then train the transfer on it (:826-881)
+            for phase in range(args.multi_num):
+                self.MF_train_onestage(args, set_t, stage_id, val=val)
+                self.MFbase.eval()
+                self.save_MF_weight(save_as="hat")
+                self.updata()
+                if phase == 0:
+                    self._real_test(now_test)
+                self.transfer_train_onestage(args, set_tt, stage_id, val=val)
+                if args.Load_W_hat:
+                    self.load_MFbase_weight(self.user_weight_hat, self.item_weight_hat)
+            self.updata()
+            return True
+
+    # ------------------------------------------------------------------ table bookkeeping
+    def updata(self):
+        """w_t = Transfer(w_{t-1}, w_hat) for EVERY row of both tables, written straight into the
+        MFbase tables (reference: model/transfer.py:884-902 + load_MFbase_weight)."""
+        t0 = time.perf_counter()
+        self.MFbase.eval()
+        self.transfer.eval()
+        if self.transfer_type != "transfer2":
+            raise TypeError("No such type transfer!!!")
+        th = self.transfer.theta
+        nu = self.transfer.variant == ops.VARIANT_CONV
+        ops.transfer_forward(self.last_user_weight, self.user_weight_hat, th[:ops.NET_STRIDE], variant=self.transfer.variant,
+                             normalize_out=nu, out=self.MFbase.user_laten.weight.data)
+        ops.transfer_forward(self.last_item_weight, self.item_weight_hat, th[ops.NET_STRIDE:], variant=self.transfer.variant,
+                             out=self.MFbase.item_laten.weight.data)
+        self.timers["updata"] += time.perf_counter() - t0
+
+    def save_MF_weight(self, save_as="last"):
+        """reference: model/transfer.py:911-943."""
+        if save_as == "last":
+            self.last_user_weight.copy_(self.MFbase.user_laten.weight.data)
+            self.last_item_weight.copy_(self.MFbase.item_laten.weight.data)
+        elif save_as == "hat":
+            self.last_user_weight_hat.copy_(self.user_weight_hat.data)
+            self.last_item_weight_hat.copy_(self.item_weight_hat.data)
+            self.user_weight_hat.copy_(self.MFbase.user_laten.weight.data)
+            self.item_weight_hat.copy_(self.MFbase.item_laten.weight.data)
+        else:
+            raise TypeError("save MFbase weight type is wrong")
+
+    def load_MFbase_weight(self, user_weight, item_weight):
+        """reference: model/transfer.py:945-959."""
+        self.MFbase.user_laten.weight.data.copy_(user_weight)
+        self.MFbase.item_laten.weight.data.copy_(item_weight)
+
+    # ------------------------------------------------------------------ whole stream
+    def run(self, args):
+        """reference: model/transfer.py:965-1029, including the final weighted summary with
+        N3 = round(n/3) and the test slice [N3:-1] that drops the last test period."""
+        pass_num = args.pass_num
+        self.summary = {}
+        for pass_id in range(pass_num):
+            stage_id = 0
+            self.dataset.reinit()
+            while 1:
+                flag = self.train_one_stage3(args, stage_id)
+                if flag:
+                    stage_id += 1
+                    if pass_id < (pass_num - 1) and stage_id >= 19:
+                        break
+                else:
+                    print(str(pass_id) + "--trained over!!!!!")
+                    test_num = np.array(self.test_num)
+                    N3 = round(test_num.shape[0] * 1 / 3)
+                    val_num = test_num[0:N3]
+                    test_num = test_num[N3:-1]
+                    recall = np.array(self.recall)
+                    ndcg = np.array(self.ndcg)
+                    print(test_num)
+                    print(recall)
+                    print(ndcg)
+                    print("include stage 0 of test:")
+                    val_num = val_num * 1.0 / val_num.sum()
+                    test_num = test_num * 1.0 / test_num.sum()
+                    for K, rl, nl in ((20, self.recall, self.ndcg), (10, self.recall_10, self.ndcg_10), (5, self.recall_5, self.ndcg_5)):
+                        recall = np.array(rl)
+                        ndcg = np.array(nl)
+                        s = dict(val_recall=(recall[0:N3] * val_num).sum(), val_ndcg=(ndcg[0:N3] * val_num).sum(),
+                                 test_recall=(recall[N3:-1] * test_num).sum(), test_ndcg=(ndcg[N3:-1] * test_num).sum())
+                        self.summary[K] = s
+                        print("val average recall@%d:" % K, s["val_recall"])
+                        print("val average ndcg@%d:" % K, s["val_ndcg"])
+                        print("test average recall@%d:" % K, s["test_recall"])
+                        print("test average ndcg@%d:" % K, s["test_ndcg"])
+                        print("\n")
+                    break

@@ -1,0 +1,155 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/sml_b200.h).
+
+All tensors are CUDA tensors owned by the caller; nothing here computes on the CPU and
+nothing falls back to PyTorch operators: a missing library or a failing call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (D, NET_STRIDE, VARIANT_COM, VARIANT_CONV, LOSS_BCE, LOSS_BPR, StepArgs, check, lib, ptr, stream)
+
+EVAL_BATCH = 1024      # evaluation2.test_model's DataLoader batch (model/transfer.py:431-435 of the reference)
+
+
+def _f32(t, name):
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32" % name)
+    return t
+
+
+def _i64(t, name):
+    if t.dtype != torch.int64:
+        raise TypeError("%s must be int64" % name)
+    return t
+
+
+# ------------------------------------------------------------------ evaluation
+def eval_candidates(user_tab, item_tab, rows):
+    """rows: int64 [n, 1+C] (user, positive, negatives...) -> (gt int32[n], eq int32[n])."""
+    _f32(user_tab, "user_tab"); _f32(item_tab, "item_tab"); _i64(rows, "rows")
+    n, w = rows.shape
+    gt = torch.empty(n, dtype=torch.int32, device=rows.device)
+    eq = torch.empty(n, dtype=torch.int32, device=rows.device)
+    check(lib().sml_eval_candidates(ptr(user_tab), ptr(item_tab), user_tab.shape[1], ptr(rows), n, rows.stride(0), w - 1,
+                                    ptr(gt), ptr(eq), stream()), "eval_candidates")
+    return gt, eq
+
+
+def eval_reduce(gt, eq, topk, batch=EVAL_BATCH, tie_loses=True):
+    """-> (hits int32[nb], ndcg float32[nb]) per batch of `batch` consecutive rows."""
+    n = gt.numel()
+    nb = (n + batch - 1) // batch
+    hits = torch.zeros(nb, dtype=torch.int32, device=gt.device)
+    ndcg = torch.zeros(nb, dtype=torch.float32, device=gt.device)
+    check(lib().sml_eval_reduce(ptr(gt), ptr(eq), n, batch, topk, int(bool(tie_loses)), ptr(hits), ptr(ndcg), stream()),
+          "eval_reduce")
+    return hits, ndcg
+
+
+def pair_scores(user_tab, item_tab, user, item, norm=False):
+    n = user.numel()
+    out = torch.empty(n, dtype=torch.float32, device=user_tab.device)
+    check(lib().sml_pair_scores(ptr(user_tab), ptr(item_tab), user_tab.shape[1], ptr(_i64(user, "user")), ptr(_i64(item, "item")),
+                                n, int(bool(norm)), ptr(out), stream()), "pair_scores")
+    return out
+
+
+# ------------------------------------------------------------------ transfer forward
+_ws_cache = {}
+
+
+def _workspace(nbytes, device, tag):
+    """Zero-initialised scratch, grown on demand and reused (keyed by device + tag)."""
+    key = (device.index, tag)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(int(nbytes), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def transfer_forward(x_t, x_hat, theta_net, variant=VARIANT_COM, ids=None, normalize_out=False, out=None, tensor_cores=None):
+    """out[n] = one_transfer(stack(x_t[i_n], x_hat[i_n])), i_n = ids[n] or n.  theta_net: flat fp32 [NET_STRIDE]."""
+    _f32(x_t, "x_t"); _f32(x_hat, "x_hat"); _f32(theta_net, "theta_net")
+    n = x_t.shape[0] if ids is None else ids.numel()
+    if out is None:
+        out = torch.empty(n, D, dtype=torch.float32, device=x_t.device)
+    l = lib()
+    use_tc = hasattr(l, "sml_transfer_fwd_tc") if tensor_cores is None else bool(tensor_cores)
+    if use_tc:
+        ws = _workspace(l.sml_transfer_fwd_tc_workspace_bytes(n), x_t.device, "fwd_tc")
+        fn = l.sml_transfer_fwd_tc
+    else:
+        ws = _workspace(l.sml_transfer_fwd_workspace_bytes(n), x_t.device, "fwd")
+        fn = l.sml_transfer_fwd
+    check(fn(ptr(x_t), ptr(x_hat), ptr(ids), n, x_t.shape[1], variant, ptr(theta_net), int(bool(normalize_out)), ptr(out),
+             ptr(ws), ws.numel(), stream()), "transfer_fwd")
+    return out
+
+
+# ------------------------------------------------------------------ optimizer
+def new_adam_state(device):
+    """[step, (step_size, sqrt(bc2)) packed as floats, spare, spare] -- see sml_adam_tick."""
+    return torch.zeros(4, dtype=torch.int64, device=device)
+
+
+def adam_tick(state, lr, beta1=0.9, beta2=0.999):
+    check(lib().sml_adam_tick(ptr(state), lr, beta1, beta2, stream()), "adam_tick")
+
+
+def adam_dense(p, m, v, g, state, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, zero_grad=True):
+    check(lib().sml_adam_dense(ptr(p), ptr(m), ptr(v), ptr(g), p.numel(), ptr(state), beta1, beta2, eps, weight_decay,
+                               int(bool(zero_grad)), stream()), "adam_dense")
+
+
+# ------------------------------------------------------------------ steps
+def step_workspace(batch, device, tag="step"):
+    return _workspace(lib().sml_step_workspace_bytes(batch), device, tag)
+
+
+def make_step_args(*, user, item, neg, last_user, last_item, hat_user, hat_item, theta, variant=VARIANT_COM, loss=LOSS_BCE,
+                   g_user=None, g_item=None, m_user=None, v_user=None, m_item=None, v_item=None, adam_state=None,
+                   lr=0.0, l2=0.0, g_theta=None, m_theta=None, v_theta=None, loss_out=None, workspace=None):
+    a = StepArgs()
+    B = user.numel()
+    a.user, a.item, a.neg, a.batch = ptr(_i64(user, "user")), ptr(_i64(item, "item")), ptr(_i64(neg, "neg")), B
+    a.last_user, a.last_item = ptr(_f32(last_user, "last_user")), ptr(_f32(last_item, "last_item"))
+    a.hat_user, a.hat_item = ptr(_f32(hat_user, "hat_user")), ptr(_f32(hat_item, "hat_item"))
+    a.n_users, a.n_items = hat_user.shape[0], hat_item.shape[0]
+    a.theta, a.variant, a.loss = ptr(_f32(theta, "theta")), variant, loss
+    a.g_user, a.g_item = ptr(g_user), ptr(g_item)
+    a.m_user, a.v_user, a.m_item, a.v_item = ptr(m_user), ptr(v_user), ptr(m_item), ptr(v_item)
+    a.adam_state, a.lr, a.l2 = ptr(adam_state), float(lr), float(l2)
+    a.g_theta, a.m_theta, a.v_theta = ptr(g_theta), ptr(m_theta), ptr(v_theta)
+    if workspace is None:
+        workspace = step_workspace(B, user.device)
+    a.loss_out, a.workspace, a.workspace_bytes = ptr(loss_out), ptr(workspace), workspace.numel()
+    # keep the tensors alive as long as the struct
+    a._keep = (user, item, neg, last_user, last_item, hat_user, hat_item, theta, g_user, g_item, m_user, v_user, m_item,
+               v_item, adam_state, g_theta, m_theta, v_theta, loss_out, workspace)
+    return a
+
+
+def mf_step(args):
+    check(lib().sml_mf_step(C.byref(args), stream()), "mf_step")
+
+
+def tr_step(args):
+    check(lib().sml_tr_step(C.byref(args), stream()), "tr_step")
+
+
+def run_mf_grads(args, d_rows=None, scores=None):
+    check(lib().sml_run_mf_grads(C.byref(args), ptr(d_rows), ptr(scores), stream()), "run_mf_grads")
+
+
+def plain_mf_grads(user_tab, item_tab, user, item, neg, g_user, g_item, loss_out, loss=LOSS_BCE, l2_u=0.0, l2_i=0.0,
+                   item_bias=None, g_item_bias=None):
+    ws = _workspace(256 + 2 * 2048 * 4, user_tab.device, "plain_mf")
+    check(lib().sml_plain_mf_grads(ptr(user_tab), ptr(item_tab), ptr(item_bias), ptr(_i64(user, "user")), ptr(_i64(item, "item")),
+                                   ptr(_i64(neg, "neg")), user.numel(), user_tab.shape[1], loss, l2_u, l2_i, ptr(g_user),
+                                   ptr(g_item), ptr(g_item_bias), ptr(loss_out), ptr(ws), ws.numel(), stream()),
+          "plain_mf_grads")

@@ -1,0 +1,272 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden fixtures generated from the
+UNMODIFIED reference and against the numpy oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): integer / index outputs (ranks, hit counts, hit rows, sampled
+triples) bit-exact; fp32 forward quantities rel 1e-5; after optimizer updates 1e-4."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sml_oracle as O
+from tests.helpers import theta_from_chk, sample, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = 1e-5
+GRAD_TOL = 5e-5
+STEP_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from sml_b200 import _lib
+    assert _lib.lib().sml_device_check() == 0, _lib.lib().sml_last_error()
+    return torch.device("cuda:0")
+
+
+def T(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def make_module(cls, tu, ti, dev):
+    with torch.random.fork_rng(devices=[]):
+        m = cls(64, 64).to(dev)
+    sd = {("user_transfer." + k): torch.from_numpy(v) for k, v in tu.items()}
+    sd.update({("item_transfer." + k): torch.from_numpy(v) for k, v in ti.items()})
+    m.load_state_dict(sd)
+    return m
+
+
+def theta_np(m, net):
+    return {k: getattr(getattr(getattr(m, net + "_transfer"), k.split(".")[0]), k.split(".")[1]).detach().cpu().numpy() for k in O.THETA_KEYS}
+
+
+# ------------------------------------------------------------------------------- evaluation
+def test_eval_golden(golden, dev):
+    from sml_b200.model.MF import MFbasemode
+    from sml_b200.evalution.evaluation2 import test_model, DeviceTestSet
+    g = golden("eval")
+    with torch.random.fork_rng(devices=[]):
+        mf = MFbasemode(30, 200, 64).to(dev)
+    mf.user_laten.weight.data.copy_(T(g["user"], dev)); mf.item_laten.weight.data.copy_(T(g["item"], dev))
+    rows = T(g["rows"], dev)
+    for K in (20, 10, 5):
+        h, nd, idx = mf.test(rows, topK=K)
+        assert h == float(g["hits@%d" % K])                               # exact
+        assert np.array_equal(idx.cpu().numpy(), g["idx@%d" % K])         # exact
+        assert abs(float(nd) - float(g["ndcg@%d" % K])) < 1e-5
+        r, n = test_model(mf, DeviceTestSet(rows, batch=16), topK=K)
+        assert abs(r - float(g["recall@%d" % K])) < 1e-12 and abs(float(n) - float(g["tm_ndcg@%d" % K])) < 1e-6
+        loader = [rows[s:s + 16] for s in range(0, rows.shape[0], 16)]   # the reference's calling convention
+        r2, n2 = test_model(mf, loader, topK=K)
+        assert abs(r2 - r) < 1e-12 and abs(float(n2) - float(n)) < 1e-6
+    # forward scores
+    u = rows[:, :1].expand(-1, rows.shape[1] - 1).reshape(-1).contiguous()
+    i = rows[:, 1:].reshape(-1).contiguous()
+    _, _, sc = mf(u, i)
+    assert rel_err(sc.cpu().numpy().reshape(g["scores"].shape), g["scores"]) < FWD_TOL
+
+
+def test_eval_vs_oracle_c1000_and_edges(dev):
+    from sml_b200 import ops
+    rng = np.random.default_rng(1)
+    U, I, N, C = 400, 3000, 777, 1000                                    # ragged N, the reference's C
+    ut = rng.standard_normal((U, 64)).astype(np.float32); it = rng.standard_normal((I, 64)).astype(np.float32)
+    rows = np.concatenate([rng.integers(0, U, (N, 1)), rng.integers(0, I, (N, C))], 1).astype(np.int64)
+    rows[5, 2:6] = rows[5, 1]                                             # exact ties with the positive
+    it[7] = np.nan; rows[9, 3] = 7                                        # a NaN candidate outranks everything
+    rows[11, 1] = 7                                                       # NaN positive
+    gt, eq = ops.eval_candidates(T(ut, dev), T(it, dev), T(rows, dev))
+    s64 = O.candidate_scores(ut.astype(np.float64), it.astype(np.float64), rows)
+    ogt, oeq = O.candidate_ranks(s64.astype(np.float32))
+    # rows whose positive is separated from every negative by > 1e-4 must be bit-exact (summation order only
+    # matters inside a few ulp); count the rest
+    with np.errstate(invalid="ignore"):
+        margin = np.nanmin(np.where(s64[:, 1:] == s64[:, :1], np.inf, np.abs(s64[:, 1:] - s64[:, :1])), axis=1)
+    safe = margin > 1e-4
+    assert safe.mean() > 0.95
+    assert np.array_equal(gt.cpu().numpy()[safe], ogt[safe])
+    assert int(eq[5]) >= 4 and int(gt[9]) >= 1
+    assert int(gt[11]) == 0                                               # nothing beats a NaN positive
+    # empty input and C = 1
+    g0, e0 = ops.eval_candidates(T(ut, dev), T(it, dev), torch.zeros(0, 1 + C, dtype=torch.int64, device=dev))
+    assert g0.numel() == 0
+    g1, e1 = ops.eval_candidates(T(ut, dev), T(it, dev), T(rows[:, :2].copy(), dev))
+    assert int(g1.sum()) == 0 and int(e1.sum()) == 0
+    hits, nd = ops.eval_reduce(gt, eq, 20, batch=1024)
+    r = (ogt + oeq)
+    assert abs(int(hits.sum()) - int((r < 20).sum())) <= int((~safe).sum())
+
+
+def test_eval_rejects_bad_args(dev):
+    from sml_b200 import ops
+    t = torch.zeros(4, 32, device=dev)
+    with pytest.raises(RuntimeError, match="unsupported"):
+        ops.eval_candidates(t, t, torch.zeros(2, 3, dtype=torch.int64, device=dev))
+    with pytest.raises(RuntimeError):
+        ops.eval_candidates(torch.zeros(4, 64), torch.zeros(4, 64), torch.zeros(2, 3, dtype=torch.int64))   # CPU tensors
+
+
+# ------------------------------------------------------------------------------- transfer forward
+def test_transfer_forward_golden(golden, dev):
+    from sml_b200.model.conv_transfer import ConvTransfer_com, ConvTransfer
+    g = golden("transfer_fwd")
+    x_t, x_hat = T(g["x_t"], dev), T(g["x_hat"], dev)
+    com = make_module(ConvTransfer_com, *theta_from_chk(g["theta_com"]), dev)
+    assert rel_err(com(x_t, x_hat, "user").cpu().numpy(), g["com_user"]) < FWD_TOL
+    assert rel_err(com(x_t, x_hat, "item").cpu().numpy(), g["com_item"]) < FWD_TOL
+    conv = make_module(ConvTransfer, *theta_from_chk(g["theta_conv"]), dev)
+    assert rel_err(conv(x_t, x_hat, "user").cpu().numpy(), g["conv_user"]) < FWD_TOL
+    assert rel_err(conv(x_t, x_hat, "item").cpu().numpy(), g["conv_item"]) < FWD_TOL
+    with pytest.raises(TypeError):
+        com(x_t, x_hat, "nobody")
+
+
+@pytest.mark.parametrize("n", [1, 63, 129, 8192 + 77])
+def test_transfer_forward_vs_oracle(dev, n):
+    from sml_b200 import ops
+    rng = np.random.default_rng(n)
+    th = O.init_theta(np.random.default_rng(3))
+    flat = flat_theta(th, dev)
+    xt = rng.standard_normal((n, 64)).astype(np.float32); xh = (0.5 * rng.standard_normal((n, 64))).astype(np.float32)
+    for tc in (False,) + ((True,) if hasattr(ops.lib(), "sml_transfer_fwd_tc") else ()):
+        y = ops.transfer_forward(T(xt, dev), T(xh, dev), flat, tensor_cores=tc).cpu().numpy()
+        assert rel_err(y, O.conv_transfer_com_forward(th, xt, xh)) < FWD_TOL, tc
+    ids = rng.integers(0, n, size=max(1, n // 2)).astype(np.int64)
+    y = ops.transfer_forward(T(xt, dev), T(xh, dev), flat, ids=T(ids, dev)).cpu().numpy()
+    assert rel_err(y, O.conv_transfer_com_forward(th, xt[ids], xh[ids])) < FWD_TOL
+
+
+def flat_theta(th, dev):
+    from sml_b200 import _lib
+    f = torch.zeros(_lib.NET_STRIDE, dtype=torch.float32)
+    for k, off in (("conv1.weight", _lib.OFF_C1W), ("conv1.bias", _lib.OFF_C1B), ("conv2.weight", _lib.OFF_C2W), ("conv2.bias", _lib.OFF_C2B),
+                   ("fc1.weight", _lib.OFF_F1W), ("fc1.bias", _lib.OFF_F1B), ("fc2.weight", _lib.OFF_F2W), ("fc2.bias", _lib.OFF_F2B)):
+        f[off:off + th[k].size] = torch.from_numpy(th[k].reshape(-1))
+    return f.to(dev)
+
+
+def test_transfer_zero_row_is_nan_like_reference(dev):
+    """x_com = x_t*x_hat/||x_t|| has no eps (conv_transfer.py:94-98): an all-zero w_{t-1} row gives NaN."""
+    from sml_b200 import ops
+    th = O.init_theta(np.random.default_rng(3))
+    xt = np.zeros((3, 64), np.float32); xt[1] = 1.0
+    xh = np.ones((3, 64), np.float32)
+    y = ops.transfer_forward(T(xt, dev), T(xh, dev), flat_theta(th, dev)).cpu().numpy()
+    assert np.isnan(y[0]).all() and np.isfinite(y[1]).all() and np.isnan(y[2]).all()
+
+
+# ------------------------------------------------------------------------------- run_MF + gradients
+@pytest.mark.parametrize("tag", ["com_bce", "com_bpr", "conv_bpr"])
+def test_run_mf_golden(golden, dev, tag):
+    from sml_b200.model.conv_transfer import ConvTransfer_com, ConvTransfer
+    g = golden("run_mf")
+    cls = ConvTransfer if tag == "conv_bpr" else ConvTransfer_com
+    m = make_module(cls, *theta_from_chk(g["theta_conv" if tag == "conv_bpr" else "theta_com"]), dev)
+    rows = {k: T(g[k], dev).requires_grad_("hat" in k) for k in ("u_last", "u_hat", "i_last", "i_hat", "j_last", "j_hat")}
+    kw = {} if tag == "conv_bpr" else dict(BCE=(tag == "com_bce"))
+    loss = m.run_MF(rows["u_last"], rows["u_hat"], rows["i_last"], rows["i_hat"], rows["j_last"], rows["j_hat"], **kw)
+    loss.backward()
+    ref = float(g[tag + ".loss"])
+    assert abs(loss.item() - ref) < FWD_TOL * max(1.0, abs(ref))
+    for k in ("u_hat", "i_hat", "j_hat"):
+        assert rel_err(rows[k].grad.cpu().numpy(), g[tag + ".d_" + k]) < GRAD_TOL, k
+    for net in ("user", "item"):
+        mod = getattr(m, net + "_transfer")
+        for k in O.THETA_KEYS:
+            a, b = k.split(".")
+            got = getattr(getattr(mod, a), b).grad.cpu().numpy()
+            ref = g["%s.g_%s.%s" % (tag, net, k)]
+            assert rel_err(sample(got).reshape(ref.shape), ref) < GRAD_TOL, (net, k)
+    # no autograd requested -> loss only
+    with torch.no_grad():
+        l2 = m.run_MF(*(rows[k].detach() for k in ("u_last", "u_hat", "i_last", "i_hat", "j_last", "j_hat")), **kw)
+    assert abs(l2.item() - loss.item()) < 1e-6
+
+
+# ------------------------------------------------------------------------------- the two hot loops
+def test_mf_steps_golden(golden, dev):
+    """3 MF steps with duplicate ids in a batch; dense Adam: rows touched earlier keep moving."""
+    from sml_b200 import ops
+    from sml_b200.model.conv_transfer import ConvTransfer_com
+    g = golden("mf_steps")
+    m = make_module(ConvTransfer_com, *theta_from_chk(g["theta_com"]), dev)
+    ut, it = T(g["user0"], dev), T(g["item0"], dev)
+    z = {k: torch.zeros_like(ut if "user" in k else it) for k in ("m_user", "v_user", "m_item", "v_item", "g_user", "g_item")}
+    loss = torch.zeros(2, device=dev)
+    state = ops.new_adam_state(dev)
+    lu, li = T(g["last_user"], dev), T(g["last_item"], dev)
+    for s in range(3):
+        u, i, j = (T(g["ids"][s, k], dev) for k in range(3))
+        a = ops.make_step_args(user=u, item=i, neg=j, last_user=lu, last_item=li, hat_user=ut, hat_item=it, theta=m.theta,
+                               adam_state=state, lr=float(g["lr"]), l2=float(g["l2"]), loss_out=loss, **z)
+        ops.mf_step(a)
+        assert abs(loss[0].item() - float(g["loss%d" % s])) < 2e-5
+        assert np.abs(ut.cpu().numpy() - g["user%d" % (s + 1)]).max() < STEP_TOL
+        assert np.abs(it.cpu().numpy() - g["item%d" % (s + 1)]).max() < STEP_TOL
+        assert float(z["g_user"].abs().max()) == 0.0 and float(z["g_item"].abs().max()) == 0.0   # re-zeroed
+    assert int(state[0]) == 3
+    assert abs(loss[1].item() - sum(float(g["loss%d" % s]) for s in range(3))) < 1e-4
+    assert rel_err(z["m_user"].cpu().numpy(), g["m_user"]) < 1e-4 and rel_err(z["v_item"].cpu().numpy(), g["v_item"]) < 1e-4
+    untouched = np.setdiff1d(np.arange(50), np.unique(g["ids"][:, 0]))
+    assert np.array_equal(ut.cpu().numpy()[untouched], g["user0"][untouched])                     # exact
+
+
+def test_tr_steps_golden(golden, dev):
+    from sml_b200 import ops
+    from sml_b200.model.conv_transfer import ConvTransfer_com
+    g = golden("tr_steps")
+    m = make_module(ConvTransfer_com, *theta_from_chk(g["theta_com"]), dev)
+    tabs = {k: T(g[k], dev) for k in ("last_user", "user_hat", "last_item", "item_hat")}
+    mm, vv = torch.zeros_like(m.theta), torch.zeros_like(m.theta)
+    loss = torch.zeros(2, device=dev)
+    state = ops.new_adam_state(dev)
+    for s in range(3):
+        u, i, j = (T(g["ids"][s, k], dev) for k in range(3))
+        a = ops.make_step_args(user=u, item=i, neg=j, last_user=tabs["last_user"], last_item=tabs["last_item"],
+                               hat_user=tabs["user_hat"], hat_item=tabs["item_hat"], theta=m.theta, adam_state=state,
+                               lr=float(g["lr"]), l2=float(g["wd"]), g_theta=m.theta_grad, m_theta=mm, v_theta=vv, loss_out=loss)
+        ops.tr_step(a)
+        assert abs(loss[0].item() - float(g["loss%d" % s])) < 2e-5
+    for net in ("user", "item"):
+        th = theta_np(m, net)
+        for k in O.THETA_KEYS:
+            ref = g["t3.%s.%s" % (net, k)]
+            assert np.abs(sample(th[k]).reshape(ref.shape) - ref).max() < STEP_TOL, (net, k)
+    assert float(m.theta_grad.abs().max()) == 0.0
+    # snapshot tables are read-only in the transfer step
+    assert np.array_equal(tabs["user_hat"].cpu().numpy(), g["user_hat"])
+
+
+def test_plain_mf_vs_oracle(dev):
+    from sml_b200 import ops
+    rng = np.random.default_rng(5)
+    U, I, B = 200, 300, 257
+    ut = (0.3 * rng.standard_normal((U, 64))).astype(np.float32); it = (0.3 * rng.standard_normal((I, 64))).astype(np.float32)
+    ib = rng.standard_normal((I, 1)).astype(np.float32); ub = rng.standard_normal((U, 1)).astype(np.float32)
+    u, i, j = (rng.integers(0, n, B).astype(np.int64) for n in (40, 60, 60))
+    lo, gu, gi = O.plain_mf_bce_grads(ut, it, u, i, j, 1e-3, 2e-3)
+    g_u, g_i = torch.zeros(U, 64, device=dev), torch.zeros(I, 64, device=dev)
+    loss = torch.zeros(2, device=dev)
+    ops.plain_mf_grads(T(ut, dev), T(it, dev), T(u, dev), T(i, dev), T(j, dev), g_u, g_i, loss, loss=ops.LOSS_BCE, l2_u=1e-3, l2_i=2e-3)
+    assert abs(loss[0].item() - float(lo)) < 2e-5
+    assert rel_err(g_u.cpu().numpy(), gu) < GRAD_TOL and rel_err(g_i.cpu().numpy(), gi) < GRAD_TOL
+    lo, gu, gi, gb = O.plain_mf_bpr_grads(ut, it, ub, ib, u, i, j)
+    g_u.zero_(); g_i.zero_(); g_b = torch.zeros(I, device=dev); loss.zero_()
+    ops.plain_mf_grads(T(ut, dev), T(it, dev), T(u, dev), T(i, dev), T(j, dev), g_u, g_i, loss, loss=ops.LOSS_BPR,
+                       item_bias=T(ib[:, 0].copy(), dev), g_item_bias=g_b)
+    assert abs(loss[0].item() - float(lo)) < 1e-4 * max(1.0, abs(float(lo)))
+    assert rel_err(g_u.cpu().numpy(), gu) < GRAD_TOL and rel_err(g_i.cpu().numpy(), gi) < GRAD_TOL
+    assert rel_err(g_b.cpu().numpy(), gb[:, 0]) < GRAD_TOL
+    # dense Adam on top (fused zero_grad)
+    m, v = torch.zeros_like(g_u), torch.zeros_like(g_u)
+    p = T(ut, dev)
+    st = ops.new_adam_state(dev)
+    ops.adam_tick(st, 0.01)
+    ops.adam_dense(p, m, v, g_u, st)
+    pn, mn, vn = ut.copy(), np.zeros_like(ut), np.zeros_like(ut)
+    O.adam_step(pn, gu, mn, vn, 1, 0.01)
+    assert np.abs(p.cpu().numpy() - pn).max() < 1e-5 and float(g_u.abs().max()) == 0.0
+EOF
+echo done

@@ -1,0 +1,155 @@
+"""Host-side logic on CPU: the period state machine and the batch streams of sml_b200.meta_train
+must consume the global RNGs exactly like the reference (--numworkers 0) and therefore produce
+bit-identical (user, item, neg) triples -- checked against the batches recorded from the
+UNMODIFIED reference by oracle/gen_golden.py.  Device work is replaced by a recording test double
+(this is a test of the host logic only; the product class has no CPU path)."""
+import argparse
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from sml_b200.data import synth
+from sml_b200.data.batching import ReferenceStream
+from sml_b200.data.dataset import offlineDataset_withsample
+from sml_b200.data.dataset2 import transfer_data, trainDataset_withPreSample
+from sml_b200.model.transfer import meta_train
+
+
+def make_args(g, tmp, stop=False):
+    mfb, trb, multi, mfe, tre, seed = (int(x) for x in g["args"])
+    lr, l2, trlr, trl2 = (float(x) for x in g["hyper"])
+    return argparse.Namespace(
+        data_name="yelp", data_path=tmp + "/", multi_num=multi, MF_lr=lr, MF_epochs=mfe, l2=l2, MF_batch_size=mfb, laten=64,
+        pre_model=os.path.join(tmp, "pre.pt"), MF_sample="all", Load_W_hat=False, clip_grad=False, need_adaptive=False,
+        maxnorm_grad=3.0, TR_lr=trlr, TR_l2=trl2, TR_epochs=tre, TR_batch_size=trb, TR_sample_type="alone",
+        TR_with_MF_bias=False, TR_stop_=stop, transfer_type="conv_com", seed=seed, numworkers=0, cuda=0, topK=20, pass_num=1,
+        norm=False, Lambda_lr=0.01, min_l2=0.0001, set_t_as_tt=False, tqdm=False, need_writer=False, test_in_TR_Train=False)
+
+
+def write_fixture_stream(g, tmp):
+    NP, U, I = int(g["n_periods"]), int(g["U"]), int(g["I"])
+    periods = [(g["train%d" % p].astype(np.int64), g["test%d" % p].astype(np.int64)) for p in range(NP)]
+    synth.write_stream(tmp + "/", "mini", periods, U, I)
+    sd = {"user_laten.weight": torch.from_numpy(g["pre_user"]), "item_laten.weight": torch.from_numpy(g["pre_item"]),
+          "user_bais.weight": torch.zeros(U, 1), "item_bais.weight": torch.zeros(I, 1)}
+    torch.save(sd, os.path.join(tmp, "pre.pt"))
+    return NP, U, I
+
+
+class HostProbe(meta_train):
+    """meta_train with every device operation replaced by a recorder."""
+
+    def _require_device(self, device):
+        self.device = torch.device("cpu")
+        self.events = []
+
+    def _test_set(self, arr):
+        return arr
+
+    def _eval(self, test_set, topK):
+        ReferenceStream.loader_iter()
+        self.events.append(("eval", test_set.shape[0], topK))
+        return 0.0, torch.tensor(0.0)
+
+    def _mf_epoch(self, args, triples):
+        self.events.append(("MF", np.stack(triples, 1)))
+        return 0.0
+
+    def _tr_epoch(self, args, triples):
+        self.events.append(("TR", np.stack(triples, 1)))
+        return 0.0
+
+    def updata(self):
+        self.events.append(("updata",))
+
+
+@pytest.mark.parametrize("name,stop", [("period_run", False), ("period_run_stop", True)])
+def test_batch_stream_matches_reference(golden, tmp_path, name, stop):
+    g = golden(name)
+    tmp = str(tmp_path)
+    NP, U, I = write_fixture_stream(g, tmp)
+    args = make_args(g, tmp, stop)
+    torch.manual_seed(args.seed); np.random.seed(args.seed + 2)       # main_yelp.py:137-140
+    ds = transfer_data(args, path=args.data_path, datasetname="mini", file_path_list=[str(i) for i in range(NP)],
+                       test_list=[str(j) for j in range(5, NP)], validation_list=None, online_train_time=2, online_test_time=5)
+    probe = HostProbe(args, ds, U, I, 64)
+    probe.run(args)
+    kinds = [str(k) for k in g["log_kinds"]]
+    got = [e for e in probe.events if e[0] in ("MF", "TR")]
+    # one reference dataset instance may span several epochs (MF_epochs = 2 in the stop branch)
+    ref = []
+    for n, kind in enumerate(kinds):
+        rec = g["log%d" % n]
+        N = 96
+        for s in range(0, len(rec), N):
+            ref.append((kind, rec[s:s + N, 1:4].astype(np.int64)))
+    assert [k for k, _ in got] == [k for k, _ in ref]
+    for (k, a), (_, b) in zip(got, ref):
+        assert np.array_equal(a, b), k                               # sampled indices: bit-exact
+    assert len(probe.test_num) == 3 and probe.test_num == [96, 96, 96]
+    n_updata = sum(1 for e in probe.events if e[0] == "updata")
+    assert n_updata > 0
+
+
+def test_presample_column_semantics():
+    """The shuffled negative-column list includes the positive column (column 1) and the column
+    advances once per full pass (data/dataset2.py:181-200)."""
+    np.random.seed(5)
+    data = np.arange(7 * 6).reshape(7, 6)
+    ds = trainDataset_withPreSample(data)
+    assert sorted(ds.neg_flag.tolist()) == [1, 2, 3, 4, 5] and ds.neg_all == 4
+    c0 = ds.current_column()
+    for i in range(7):
+        u, it, ng = ds[i]
+        assert ng == data[i, c0]
+    assert ds.used_neg_count == 1 and ds.current_column() == int(ds.neg_flag[1])
+
+
+def test_alone_sampler_vectorised_equals_sequential():
+    rng = np.random.default_rng(0)
+    data = np.stack([rng.integers(0, 20, 300), rng.integers(0, 15, 300)], 1)
+    order = rng.permutation(300)
+    np.random.seed(9)
+    ds = offlineDataset_withsample(data)
+    seq = np.array([ds[i][2] for i in order])
+    state_after_seq = np.random.get_state()[1].copy()
+    np.random.seed(9)
+    vec = ReferenceStream.alone_negatives(ds, order)
+    assert np.array_equal(seq, vec)
+    assert np.array_equal(state_after_seq, np.random.get_state()[1])   # same number of draws consumed
+    assert not ds.interacted(ds.user[order], vec).any()
+
+
+def test_next_train_branches(golden, tmp_path):
+    g = golden("period_run")
+    tmp = str(tmp_path)
+    NP, U, I = write_fixture_stream(g, tmp)
+    args = make_args(g, tmp)
+    ds = transfer_data(args, path=args.data_path, datasetname="mini", file_path_list=[str(i) for i in range(NP)],
+                       test_list=[str(j) for j in range(5, NP)], online_train_time=2, online_test_time=5)
+    assert int(ds.user_number) == U and int(ds.item_number) == I
+    a = ds.next_train(0)
+    assert a[2] is None and a[1].shape[1] == 2 and a[0].shape[1] == 42      # train-only branch: set_tt = train file
+    b = ds.next_train(2)
+    assert b[2] is not None and np.array_equal(b[2], g["test5"])            # test+train branch
+    assert ds.next_train(5) == (None, None, None, None)                      # end of stream
+    args.TR_stop_ = True
+    ds2 = transfer_data(args, path=args.data_path, datasetname="mini", file_path_list=[str(i) for i in range(NP)],
+                        test_list=[str(j) for j in range(5, NP)], online_train_time=2, online_test_time=5)
+    c = ds2.next_train(2)
+    assert c[1] is None and c[3] is c[2]                                     # stop-transfer branch
+
+
+def test_synth_stream_layout(tmp_path):
+    periods = synth.make_stream(50, 80, 40, 3, n_neg=20, seed=1)
+    root = synth.write_stream(str(tmp_path) + "/", "s", periods, 50, 80)
+    info = np.load(os.path.join(root, "information.npy"))
+    assert info.tolist() == [120, 50, 80]
+    te = np.load(os.path.join(root, "test", "1.npy"))
+    assert te.shape == (40, 22) and te.dtype == np.int64
+    for row in te:
+        assert len(set(row[2:].tolist())) == 20 and row[1] not in row[2:]
+    churn = synth.make_stream(60, 400, 50, 4, n_neg=20, seed=2, churn=0.5)
+    assert all(t.shape == (50, 22) for _, t in churn)
