@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- periods/s of the SML per-period retraining hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is ONE SML PERIOD of configs[1] (Yelp-shaped synthetic stream, ConvTransfer_com,
+main_yelp.py defaults: multi_num=10, MF_epochs=1, TR_epochs=1, MF batch 1024, TR batch 256, 1 positive
++ 999 negatives per evaluation row): 10 x (MF epoch, w_hat snapshot, full-table transfer, transfer
+epoch) with the reference's 40 validation passes and 21 full-table transfers.
+
+  value  : periods/s with every period array AND every epoch's (u,i,j) triples already resident in
+           HBM when the timed region starts (CUDA-event time, barrier + synchronize on both sides).
+  e2e    : the same periods through the reference-facing API (meta_train.train_one_stage3) with HOST
+           numpy period arrays: host->device copies of the period files and of every epoch's sampled
+           triples, and the device->host reads of every loss / recall / ndcg are inside the timed region.
+  roofline / kernels : per-kernel CUDA-event timings taken live inside the timed region.
+  cpu_baseline : oracle/torch_port.py (stock-PyTorch CPU port of the reference loop; /root/reference
+           cannot travel to the GPU box) on a bounded sample, composed to periods/s.
+  --impl reference : the same CPU port as the reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+YELP = dict(n_users=59082, n_items=122816, rows=75000, n_neg=999)
+HYPER = dict(multi_num=10, MF_epochs=1, TR_epochs=1, MF_batch_size=1024, TR_batch_size=256, MF_lr=0.01, l2=1e-6, TR_lr=0.001,
+             TR_l2=1e-4, topK=20)
+EVAL_BYTES_PER_ROW = (1 + 1000) * 256 + 1001 * 8          # 264 264 B per test row
+TRANSFER_FLOP_PER_ROW = 403456
+TRANSFER_BYTES_PER_ROW = 768
+
+
+def make_args(**over):
+    a = argparse.Namespace(
+        data_name="yelp", data_path="", pre_model="", MF_sample="all", Load_W_hat=False, clip_grad=False, need_adaptive=False,
+        maxnorm_grad=3.0, TR_sample_type="alone", TR_with_MF_bias=False, TR_stop_=False, transfer_type="conv_com", seed=2000,
+        numworkers=0, cuda=0, pass_num=1, norm=False, Lambda_lr=0.01, min_l2=0.0001, set_t_as_tt=False, tqdm=False,
+        need_writer=False, test_in_TR_Train=False, laten=64, **HYPER)
+    for k, v in over.items():
+        setattr(a, k, v)
+    return a
+
+
+def period_counts(rows, h=HYPER):
+    mf_steps = -(-rows // h["MF_batch_size"]) * h["MF_epochs"] * h["multi_num"]
+    tr_steps = -(-rows // h["TR_batch_size"]) * h["TR_epochs"] * h["multi_num"]
+    updata = h["multi_num"] * (1 + h["TR_epochs"]) + 1
+    evals = h["multi_num"] * (1 + h["MF_epochs"] + 1 + h["TR_epochs"])
+    return mf_steps, tr_steps, updata, evals
+
+
+def synth_periods(n, shape, seed):
+    from sml_b200.data import synth
+    return synth.make_stream(shape["n_users"], shape["n_items"], shape["rows"], n, n_neg=shape["n_neg"], seed=seed,
+                             track_history=False)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.lines.append(line.strip())
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        busy = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": float(max(power))}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU port (cpu_baseline leg and --impl reference)
+# --------------------------------------------------------------------------------------------
+def cpu_port_periods_per_s(shape, seed=0, scale=1.0, verbose=False):
+    """Times oracle/torch_port.Port on a bounded sample of one Yelp-shaped period and composes the
+    per-unit times into one period (counts from period_counts)."""
+    import torch
+    from oracle import sml_oracle as O
+    from oracle.torch_port import Port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rng = np.random.default_rng(seed)
+    U, I, R = shape["n_users"], shape["n_items"], shape["rows"]
+    user0 = rng.standard_normal((U, 64), dtype=np.float32); item0 = rng.standard_normal((I, 64), dtype=np.float32)
+    p = Port(user0, item0, O.init_theta(np.random.default_rng(1)), O.init_theta(np.random.default_rng(2)),
+             mf_lr=HYPER["MF_lr"], l2=HYPER["l2"], tr_lr=HYPER["TR_lr"], tr_l2=HYPER["TR_l2"])
+    n_mf, n_tr = max(2, int(24 * scale)), max(4, int(80 * scale))
+    n_up, n_ev = int(min(U, 49152 * scale)), int(6144 * scale)
+    Bm, Bt = HYPER["MF_batch_size"], HYPER["TR_batch_size"]
+    ids = lambda B: (rng.integers(0, U, B), rng.integers(0, I, B), rng.integers(0, I, B))
+    rows = np.concatenate([rng.integers(0, U, (n_ev, 1)), rng.integers(0, I, (n_ev, 1000))], 1)
+    p.mf_step(*ids(Bm)); p.tr_step(*ids(Bt))                      # warm-up (allocator, thread pool)
+    t = time.perf_counter()
+    for _ in range(n_mf):
+        p.mf_step(*ids(Bm))
+    t_mf = (time.perf_counter() - t) / n_mf
+    t = time.perf_counter()
+    for _ in range(n_tr):
+        p.tr_step(*ids(Bt))
+    t_tr = (time.perf_counter() - t) / n_tr
+    t = time.perf_counter()
+    n_rows_up = p.updata(max_rows=n_up)
+    t_up_row = (time.perf_counter() - t) / n_rows_up
+    t = time.perf_counter()
+    p.test_model(rows, HYPER["topK"])
+    t_ev_row = (time.perf_counter() - t) / n_ev
+    mf_steps, tr_steps, n_updata, n_evals = period_counts(R)
+    t_period = mf_steps * t_mf + tr_steps * t_tr + n_updata * (U + I) * t_up_row + n_evals * R * t_ev_row
+    sample = ("%d MF steps (B=%d, dense Adam on %dx64+%dx64), %d TR steps (B=%d), transfer of %d rows, candidate eval of %d rows "
+              "x 1000; composed to one period = %d MF + %d TR steps + %d full-table transfers + %d evals of %d rows"
+              % (n_mf, Bm, U, I, n_tr, Bt, n_rows_up, n_ev, mf_steps, tr_steps, n_updata, n_evals, R))
+    detail = dict(mf_step_ms=t_mf * 1e3, tr_step_ms=t_tr * 1e3, transfer_rows_per_s=1.0 / t_up_row, eval_rows_per_s=1.0 / t_ev_row,
+                  period_s=t_period)
+    if verbose:
+        print(json.dumps(detail), file=sys.stderr)
+    return 1.0 / t_period, cores, sample, detail
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, t0 = [], time.perf_counter()
+    for s in range(a.warmup + a.steps):
+        v, cores, sample, detail = cpu_port_periods_per_s(YELP, seed=s, scale=0.5)
+        if s >= a.warmup:
+            vals.append(v)
+    v = float(np.mean(vals))
+    out = {"impl": "reference", "metric": "periods/sec", "value": v, "unit": "periods/s", "n_gpus": a.gpus, "steps": a.steps,
+           "warmup": a.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "configs[1]: Yelp-shaped SML period (U=59082, I=122816, 75000 rows, multi_num=10, ConvTransfer_com), CPU port",
+                      "note": "each step is a bounded sample composed to one period"},
+           "cpu_baseline": {"value": v, "unit": "periods/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": "periods/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(out))
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from sml_b200 import ops
+    from sml_b200._lib import lib
+    from sml_b200.data.batching import ReferenceStream, mf_epoch_triples, tr_epoch_triples
+    from sml_b200.data.dataset import offlineDataset_withsample
+    from sml_b200.data.dataset2 import trainDataset_withPreSample
+    from sml_b200.data.memory_stream import MemoryStream
+    from sml_b200.model import MF
+    from sml_b200.model.transfer import meta_train
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib()
+    quiet = open(os.devnull, "w")
+
+    W, K = a.warmup, a.steps
+    shape = dict(YELP)
+    if a.rows:
+        shape["rows"] = a.rows
+    # weak scaling: every rank retrains its own replica of the stream shard (independent period streams)
+    n_periods = 2 * (W + K) + 1
+    periods = synth_periods(n_periods, shape, seed=100 + rank)
+    U, I = shape["n_users"], shape["n_items"]
+    args = make_args()
+    torch.manual_seed(args.seed + rank); np.random.seed(args.seed + 2 + rank)
+    pre = MF.MFbasemode(U, I, 64)
+    args.pre_model = "/tmp/sml_bench_pre_%d.pt" % rank
+    torch.save(pre.state_dict(), args.pre_model)
+
+    stdout = sys.stdout
+    sys.stdout = quiet                                   # the drop-in prints like the reference; keep the JSON line clean
+    try:
+        # ---------------- e2e arm: host arrays, H2D/D2H inside the timed region ----------------
+        pin = lambda x: torch.from_numpy(x).pin_memory().numpy()          # inputs live in pinned host memory
+        e2e_periods = [(pin(tr), pin(te)) for tr, te in periods[:W + K + 1]]
+        ds = MemoryStream(e2e_periods, U, I)
+        meta = meta_train(args, ds, U, I, 64, device=dev)
+        h2d = [0]
+        orig_to_device, orig_upload = meta._to_device, meta._upload
+
+        def to_device(arr):
+            if id(arr) not in meta._dev_cache:
+                h2d[0] += arr.size * 8
+            return orig_to_device(arr)
+
+        def upload(arrs):
+            h2d[0] += sum(int(np.asarray(x).size) * 8 for x in arrs)
+            return orig_upload(arrs)
+        meta._to_device, meta._upload = to_device, upload
+        stage = 0
+        for _ in range(W):
+            meta._dev_cache.clear()
+            meta.train_one_stage3(args, stage); stage += 1
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        h2d[0] = 0
+        t0 = time.perf_counter()
+        for _ in range(K):
+            meta._dev_cache.clear()                      # nothing of this period is resident when its step starts
+            meta.train_one_stage3(args, stage); stage += 1
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        mf_steps, tr_steps, n_updata, n_evals = period_counts(shape["rows"])
+        e2e_h2d = h2d[0] / K
+        e2e_d2h = (n_evals * 8 + (HYPER["multi_num"] * (HYPER["MF_epochs"] + HYPER["TR_epochs"])) * 4)
+        if world > 1:
+            t = torch.tensor([e2e_s], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t)
+        del meta, e2e_periods
+
+        # ---------------- resident arm: everything in HBM before the clock starts ----------------
+        res_periods = periods[W + K:]
+        ds = MemoryStream(res_periods, U, I)
+        torch.manual_seed(args.seed + rank); np.random.seed(args.seed + 2 + rank)
+        meta = meta_train(args, ds, U, I, 64, device=dev, emulate_reference_rng=False)
+        meta.dev_cache_cap = 4 * len(res_periods)
+        for tr, te in res_periods:
+            meta._to_device(tr); meta._to_device(te)
+        # pre-sample every epoch's triples with the same host logic and park them on the device
+        plan = {}
+        for st in range(W + K):
+            set_t, set_tt = res_periods[st][1], res_periods[st + 1][0]
+            tt_ds = offlineDataset_withsample(set_tt)
+            for ph in range(HYPER["multi_num"]):
+                t_ds = trainDataset_withPreSample(set_t)
+                for ep in range(HYPER["MF_epochs"]):
+                    order = np.random.permutation(len(set_t))
+                    plan.setdefault(("MF", st), []).append([torch.from_numpy(x).to(dev) for x in mf_epoch_triples(t_ds, order)])
+                for ep in range(HYPER["TR_epochs"]):
+                    order = np.random.permutation(len(set_tt))
+                    plan.setdefault(("TR", st), []).append([torch.from_numpy(x).to(dev) for x in tr_epoch_triples(tt_ds, order)])
+        cursor = {}
+
+        def batch_source(kind, stage_id, epoch, n_rows):
+            k = (kind, stage_id)
+            i = cursor.get(k, 0)
+            cursor[k] = i + 1
+            return plan[k][i]
+        meta.batch_source = batch_source
+        stage = 0
+        for _ in range(W):
+            meta.train_one_stage3(args, stage); stage += 1
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        meta.events.enabled = True
+        sampler = ClockSampler(local)
+        sampler.start()
+        launches0 = lib().sml_launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(K):
+            meta.train_one_stage3(args, stage); stage += 1
+        ev1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        dev_s = ev0.elapsed_time(ev1) / 1e3
+        clocks = sampler.stop()
+        launches = lib().sml_launch_count() - launches0
+        phases = meta.events.summary()
+        meta.events.enabled = False
+        if world > 1:
+            t = torch.tensor([dev_s], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); dev_s = float(t)
+            t = torch.tensor([float(launches)], device=dev); dist.all_reduce(t); launches = int(t)
+
+        # ---------------- per-kernel CUDA-event timings on the same tables ----------------
+        kern = {}
+        val_rows = meta._to_device(res_periods[-1][1])
+        uw, iw = meta.MFbase.user_laten.weight.data, meta.MFbase.item_laten.weight.data
+
+        def time_kernel(fn, reps):
+            fn(); torch.cuda.synchronize()
+            evs = []
+            for _ in range(reps):
+                x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                x.record(); fn(); y.record(); evs.append((x, y))
+            torch.cuda.synchronize()
+            return float(np.mean([x.elapsed_time(y) for x, y in evs]))
+        ms = time_kernel(lambda: ops.eval_candidates(uw, iw, val_rows), 5)
+        kern["eval_candidates"] = dict(ms=ms, rows=int(val_rows.shape[0]), gbs=val_rows.shape[0] * EVAL_BYTES_PER_ROW / ms / 1e6)
+        th = meta.transfer.theta
+        out_u = torch.empty_like(uw)
+        ms = time_kernel(lambda: ops.transfer_forward(meta.last_user_weight, meta.user_weight_hat, th[:ops.NET_STRIDE], out=out_u), 5)
+        kern["transfer_forward"] = dict(ms=ms, rows=U, tflops=U * TRANSFER_FLOP_PER_ROW / ms / 1e9, gbs=U * TRANSFER_BYTES_PER_ROW / ms / 1e6)
+    finally:
+        sys.stdout = stdout
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    ev_n, ev_ms = phases.get("eval", (0, 0.0))
+    per_eval_ms = ev_ms / max(ev_n, 1)
+    ach = shape["rows"] * EVAL_BYTES_PER_ROW / max(per_eval_ms, 1e-9) / 1e6
+    value = world * K / dev_s
+    out = {
+        "metric": "periods/sec", "value": value, "unit": "periods/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": dev_s / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: Yelp-shaped SML period stream, ConvTransfer_com, one period per step",
+                   "n_users": U, "n_items": I, "rows_per_period": shape["rows"], "candidates_per_eval_row": 1000, **HYPER,
+                   "l2_flush": "inputs larger than L2: each step streams 2 x 600 MB period files and 47 MB x 7 table copies",
+                   "parallelism": "1 replica stream per GPU" if world > 1 else "single GPU"},
+        "samples_per_s": world * K * (HYPER["multi_num"] * shape["rows"] * (HYPER["MF_epochs"] + HYPER["TR_epochs"])) / dev_s,
+        "e2e": {"value": world * K / e2e_s, "unit": "periods/s", "h2d_bytes_per_step": int(e2e_h2d), "d2h_bytes_per_step": int(e2e_d2h)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "phases_ms_per_period": {k: v[1] / K for k, v in phases.items()},
+        "phase_counts_per_period": {k: v[0] / K for k, v in phases.items()},
+        "kernels": kern,
+        "roofline": {"kernel": "k_eval_candidates", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "note": "algorithmic bytes = 264264 B x rows per launch; the 31 MB item table is L2 resident so frac can exceed 1"},
+    }
+    if rank == 0:
+        if world == 1 and not a.no_cpu_baseline:
+            v, cores, sample, detail = cpu_port_periods_per_s(YELP, seed=0, scale=1.0)
+            out["cpu_baseline"] = {"value": v, "unit": "periods/s", "cores": cores, "kind": "port", "sample": sample, "detail": detail}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=0, help="rows per period (default: the Yelp shape, 75000)")
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

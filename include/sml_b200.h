@@ -81,6 +81,8 @@ const char *sml_last_error(void);
 int sml_device_check(void);
 /* Number of SMs on the current device (grid sizing in the host code). */
 int sml_sm_count(void);
+/* Kernels this library has launched in this process so far (bench.py's gpu_launches evidence). */
+uint64_t sml_launch_count(void);
 
 /* ---- candidate-list evaluation ---------------------------------------------------
  * Replaces MFbasemode.test (model/MF.py:45-80): rows[n, 0] = user id, rows[n, 1..C] =
@@ -165,10 +167,24 @@ int sml_mf_step(const sml_step_args *args, void *stream);
 /* HOT LOOP B body, model/transfer.py:701-728: same forward on snapshot rows, theta
  * gradients only, Adam with coupled L2 on theta. */
 int sml_tr_step(const sml_step_args *args, void *stream);
+/* One whole epoch of either loop: args->user/item/neg hold n_total triples in batch order and
+ * args->batch is the nominal batch size; steps ceil(n_total / batch) times (the last batch may be
+ * short, like DataLoader(drop_last=False), model/transfer.py:439-443,692-696) without returning to
+ * the host language between steps.  loss_out[1] accumulates the per-step losses. */
+int sml_mf_epoch(const sml_step_args *args, int64_t n_total, void *stream);
+int sml_tr_epoch(const sml_step_args *args, int64_t n_total, void *stream);
 /* Forward + loss + gradients without any optimizer update (ConvTransfer_com.run_MF +
  * backward, model/conv_transfer.py:113-135): writes d_rows [3B,64] = dL/d x_hat rows (no l2
  * term) if non-null and accumulates theta gradients into args->g_theta if non-null. */
 int sml_run_mf_grads(const sml_step_args *args, float *d_rows, float *scores /* [2B] s+, s- or null */, void *stream);
+
+/* ---- GEMM building block (exposed for tests and profiling) ---------------------------------
+ * C[M,N] = epi(opA(A) opB(B)) with the fc-layer GEMM kernels the steps use.  a_mode: 0 A[m][k], 1 same
+ * with GELU applied on load, 2 A[k][m], 3 A[k][m] + GELU.  b_mode: 0 B[n][k], 1 B[k][n], 2 B[k][n] + GELU.
+ * epi: 0 store, 1 + bias[n], 2 * GELU'(aux[m][n]), 3 accumulate into C.  tensor_cores != 0 selects the
+ * tcgen05 3xTF32 kernel (bn = 64 | 128, optional transposed store C[n][m]), 0 the SIMT fp32 kernel. */
+int sml_debug_gemm(const float *A, const float *B, const float *bias, const float *aux, float *C, int M, int N, int K, int lda,
+                   int ldb, int ldc, int a_mode, int b_mode, int epi, int transpose_out, int bn, int tensor_cores, void *stream);
 
 /* ---- plain MF steps (baselines / MF2; north_star kernel 1) ---------------------------
  * model/baseline.py:188-201 (BCE, mean, separate l2_u / l2_i) and MF2.forward

@@ -41,6 +41,7 @@ _PROTOS = {
     "sml_last_error": (C.c_char_p, []),
     "sml_device_check": (_i32, []),
     "sml_sm_count": (_i32, []),
+    "sml_launch_count": (C.c_uint64, []),
     "sml_eval_candidates": (_i32, [_vp, _vp, _i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp]),
     "sml_eval_reduce": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),
     "sml_pair_scores": (_i32, [_vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _vp]),
@@ -51,7 +52,10 @@ _PROTOS = {
     "sml_step_workspace_bytes": (_sz, [_i64]),
     "sml_mf_step": (_i32, [C.POINTER(StepArgs), _vp]),
     "sml_tr_step": (_i32, [C.POINTER(StepArgs), _vp]),
+    "sml_mf_epoch": (_i32, [C.POINTER(StepArgs), _i64, _vp]),
+    "sml_tr_epoch": (_i32, [C.POINTER(StepArgs), _i64, _vp]),
     "sml_run_mf_grads": (_i32, [C.POINTER(StepArgs), _vp, _vp, _vp]),
+    "sml_debug_gemm": (_i32, [_vp, _vp, _vp, _vp, _vp] + [_i32] * 12 + [_vp]),
     "sml_plain_mf_grads": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 

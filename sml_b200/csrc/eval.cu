@@ -146,12 +146,12 @@ int sml_eval_candidates(const float *user_tab, const float *item_tab, int d, con
     int rc = sml_check_device();
     if (rc) return rc;
     SML_REQUIRE(d == SML_D, SML_E_UNSUPPORTED, "sml_eval_candidates: d=%d unsupported (d must be %d)", d, SML_D);
+    SML_REQUIRE(n_rows >= 0, SML_E_BADARG, "sml_eval_candidates: negative n_rows");
+    if (n_rows == 0) return SML_OK;   // empty test file: nothing to do (pointers of empty tensors may be null)
     SML_REQUIRE(user_tab && item_tab && rows && gt && eq, SML_E_BADARG, "sml_eval_candidates: null pointer");
     SML_REQUIRE(n_cand >= 1 && row_stride >= 1 + (int64_t)n_cand, SML_E_BADARG,
                 "sml_eval_candidates: need n_cand >= 1 and row_stride >= 1 + n_cand (got %d, %lld)", n_cand,
                 (long long)row_stride);
-    SML_REQUIRE(n_rows >= 0, SML_E_BADARG, "sml_eval_candidates: negative n_rows");
-    if (n_rows == 0) return SML_OK;
     const size_t smem = (size_t)n_cand * sizeof(int64_t);
     SML_REQUIRE(smem <= 200 * 1024, SML_E_UNSUPPORTED, "sml_eval_candidates: n_cand=%d too large", n_cand);
     if (smem > 48 * 1024)
@@ -169,9 +169,9 @@ int sml_eval_reduce(const int32_t *gt, const int32_t *eq, int64_t n_rows, int ba
                     int32_t *hits, float *ndcg, void *stream) {
     int rc = sml_check_device();
     if (rc) return rc;
-    SML_REQUIRE(gt && eq && hits && ndcg, SML_E_BADARG, "sml_eval_reduce: null pointer");
     SML_REQUIRE(batch >= 1 && topk >= 1 && n_rows >= 0, SML_E_BADARG, "sml_eval_reduce: bad batch/topk/n_rows");
     if (n_rows == 0) return SML_OK;
+    SML_REQUIRE(gt && eq && hits && ndcg, SML_E_BADARG, "sml_eval_reduce: null pointer");
     const int64_t nb = (n_rows + batch - 1) / batch;
     k_eval_reduce<<<(int)nb, 256, 0, (cudaStream_t)stream>>>(gt, eq, n_rows, batch, topk, tie_loses, hits, ndcg);
     SML_LAUNCH_OK();

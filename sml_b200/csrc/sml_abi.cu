@@ -1,5 +1,6 @@
 // ABI plumbing: version, thread-local error string, device check.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "sml_common.cuh"
@@ -13,6 +14,21 @@ void sml_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+void sml_note_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
+int sml_use_tensor_cores() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SML_GEMM");
+        v = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+    }
+    return v;
+}
+
+static int g_dev_ok[64];     // per-device cache: 1 = verified sm_100-class
+static int g_sm_count[64];
+
 int sml_check_device() {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -20,6 +36,7 @@ int sml_check_device() {
         sml_set_error("cudaGetDevice: %s (no CUDA device: libsml_b200 has no CPU path)", cudaGetErrorString(e));
         return SML_E_CUDA;
     }
+    if (dev >= 0 && dev < 64 && g_dev_ok[dev]) return SML_OK;
     int major = 0;
     e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
     if (e != cudaSuccess) {
@@ -30,6 +47,7 @@ int sml_check_device() {
         sml_set_error("device %d has compute capability %d.x; libsml_b200 is built for sm_100a only", dev, major);
         return SML_E_ARCH;
     }
+    if (dev >= 0 && dev < 64) g_dev_ok[dev] = 1;
     return SML_OK;
 }
 
@@ -41,10 +59,14 @@ const char *sml_last_error(void) { return g_err; }
 
 int sml_device_check(void) { return sml_check_device(); }
 
+uint64_t sml_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 int sml_sm_count(void) {
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (dev >= 0 && dev < 64 && g_sm_count[dev]) return g_sm_count[dev];
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (dev >= 0 && dev < 64) g_sm_count[dev] = n;
     return n;
 }
 

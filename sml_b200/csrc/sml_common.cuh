@@ -10,6 +10,7 @@
 
 void sml_set_error(const char *fmt, ...);
 int sml_check_device();
+void sml_note_launch();   // bumps the kernel-launch counter read by sml_launch_count()
 
 #define SML_CUDA_OK(expr)                                                                        \
     do {                                                                                         \
@@ -27,6 +28,7 @@ int sml_check_device();
             sml_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
             return SML_E_CUDA;                                                                   \
         }                                                                                        \
+        sml_note_launch();                                                                       \
     } while (0)
 
 #define SML_REQUIRE(cond, code, ...)                                                             \
@@ -79,7 +81,7 @@ int sml_launch_conv_bwd(const SmlConvBwdGroup *groups, int n_groups, int variant
                         float *d_rows, cudaStream_t st);
 
 // Generic SIMT fp32 GEMM (grouped over blockIdx.z):  C[M,N] = epi(opA(A)[M,K] * opB(B)[K,N])
-enum { SML_A_MK = 0, SML_A_MK_GELU = 1, SML_A_KM = 2 };         // A stored [m][k] / same + gelu on load / [k][m]
+enum { SML_A_MK = 0, SML_A_MK_GELU = 1, SML_A_KM = 2, SML_A_KM_GELU = 3 };   // A stored [m][k] / + gelu on load / [k][m] / + gelu
 enum { SML_B_NK = 0, SML_B_KN = 1, SML_B_KN_GELU = 2 };         // B stored [n][k] / [k][n] / [k][n] + gelu on load
 enum { SML_EPI_NONE = 0, SML_EPI_BIAS = 1, SML_EPI_MUL_GELU_GRAD = 2, SML_EPI_ACCUM = 3 };
 struct SmlGemmProb {
@@ -88,6 +90,11 @@ struct SmlGemmProb {
     int M, N, K, lda, ldb, ldc;
 };
 int sml_launch_sgemm(const SmlGemmProb *probs, int n_probs, int a_mode, int b_mode, int epi, cudaStream_t st);
+// tcgen05 3xTF32 GEMM, same contract (+ transposed store: C[n][m]); bn = 64 | 128
+int sml_launch_umma_gemm(const SmlGemmProb *probs, int n_probs, int a_mode, int b_mode, int epi, int transpose_out, int bn,
+                         cudaStream_t st);
+// 1 = tensor-core GEMMs (default), 0 = SIMT fp32 GEMMs (SML_GEMM=simt in the environment, for A/B comparisons)
+int sml_use_tensor_cores();
 
 // column sums: out[c] (+)= sum_r X[r, c]   (bias gradients)
 struct SmlColsumProb { const float *X; float *out; int rows, cols, ld; };

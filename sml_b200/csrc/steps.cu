@@ -7,6 +7,12 @@ namespace {
 
 constexpr int64_t FWD_CHUNK = 8192;   // rows per pass of the SIMT transfer forward
 
+// fc GEMM dispatch: tcgen05 3xTF32 by default, SIMT fp32 when SML_GEMM=simt
+int gemm(const SmlGemmProb *probs, int n, int a_mode, int b_mode, int epi, int bn, cudaStream_t st) {
+    if (sml_use_tensor_cores()) return sml_launch_umma_gemm(probs, n, a_mode, b_mode, epi, 0, bn, st);
+    return sml_launch_sgemm(probs, n, a_mode, b_mode, epi, st);
+}
+
 struct StepWs {
     unsigned int *ticket;   // [64] (only [0] used), re-armed by k_loss
     float *partials;        // [3 * 1024]
@@ -70,13 +76,13 @@ int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, f
     SmlGemmProb fc1[2] = {
         {w.A, tu + SML_OFF_F1W, tu + SML_OFF_F1B, nullptr, w.Z1, (int)B, 512, 320, 320, 320, 512},
         {w.A + B * 320, ti + SML_OFF_F1W, ti + SML_OFF_F1B, nullptr, w.Z1 + B * 512, (int)(2 * B), 512, 320, 320, 320, 512}};
-    rc = sml_launch_sgemm(fc1, 2, SML_A_MK, SML_B_NK, SML_EPI_BIAS, st);
+    rc = gemm(fc1, 2, SML_A_MK, SML_B_NK, SML_EPI_BIAS, 128, st);
     if (rc) return rc;
     // fc2: Y = g(Z1) W2^T + b2   (:48-49)
     SmlGemmProb fc2[2] = {
         {w.Z1, tu + SML_OFF_F2W, tu + SML_OFF_F2B, nullptr, w.Y, (int)B, 64, 512, 512, 512, 64},
         {w.Z1 + B * 512, ti + SML_OFF_F2W, ti + SML_OFF_F2B, nullptr, w.Y + B * 64, (int)(2 * B), 64, 512, 512, 512, 64}};
-    rc = sml_launch_sgemm(fc2, 2, SML_A_MK_GELU, SML_B_NK, SML_EPI_BIAS, st);
+    rc = gemm(fc2, 2, SML_A_MK_GELU, SML_B_NK, SML_EPI_BIAS, 64, st);
     if (rc) return rc;
     rc = sml_launch_loss(w.Y, want_rowsq ? w.rowsq : nullptr, B, a->loss, a->variant == SML_VARIANT_CONV, l2, w.dY, scores,
                          a->loss_out, w.partials, w.ticket, st);
@@ -85,7 +91,7 @@ int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, f
     SmlGemmProb d2[2] = {
         {w.dY, tu + SML_OFF_F2W, nullptr, w.Z1, w.dZ1, (int)B, 512, 64, 64, 512, 512},
         {w.dY + B * 64, ti + SML_OFF_F2W, nullptr, w.Z1 + B * 512, w.dZ1 + B * 512, (int)(2 * B), 512, 64, 64, 512, 512}};
-    return sml_launch_sgemm(d2, 2, SML_A_MK, SML_B_KN, SML_EPI_MUL_GELU_GRAD, st);
+    return gemm(d2, 2, SML_A_MK, SML_B_KN, SML_EPI_MUL_GELU_GRAD, 128, st);
 }
 
 int fc1_dgrad(const sml_step_args *a, const StepWs &w, cudaStream_t st) {
@@ -94,7 +100,7 @@ int fc1_dgrad(const sml_step_args *a, const StepWs &w, cudaStream_t st) {
     SmlGemmProb d1[2] = {
         {w.dZ1, tu + SML_OFF_F1W, nullptr, nullptr, w.dA, (int)B, 320, 512, 512, 320, 320},
         {w.dZ1 + B * 512, ti + SML_OFF_F1W, nullptr, nullptr, w.dA + B * 320, (int)(2 * B), 320, 512, 512, 320, 320}};
-    return sml_launch_sgemm(d1, 2, SML_A_MK, SML_B_KN, SML_EPI_NONE, st);
+    return gemm(d1, 2, SML_A_MK, SML_B_KN, SML_EPI_NONE, 64, st);
 }
 
 // fc1/fc2 weight + bias gradients accumulated into g_theta  (theta grads of conv_transfer.py:47-49)
@@ -104,12 +110,21 @@ int fc_wgrads(const sml_step_args *a, const StepWs &w, float *g_theta, cudaStrea
     SmlGemmProb w2[2] = {
         {w.dY, w.Z1, nullptr, nullptr, gu + SML_OFF_F2W, 64, 512, (int)B, 64, 512, 512},
         {w.dY + B * 64, w.Z1 + B * 512, nullptr, nullptr, gi + SML_OFF_F2W, 64, 512, (int)(2 * B), 64, 512, 512}};
-    int rc = sml_launch_sgemm(w2, 2, SML_A_KM, SML_B_KN_GELU, SML_EPI_ACCUM, st);
+    int rc;
+    if (sml_use_tensor_cores()) {
+        // tensor-core tiles are 128 rows tall: compute dW2^T [512, 64] = g(Z1)^T dY and store it transposed
+        SmlGemmProb w2t[2] = {
+            {w.Z1, w.dY, nullptr, nullptr, gu + SML_OFF_F2W, 512, 64, (int)B, 512, 64, 512},
+            {w.Z1 + B * 512, w.dY + B * 64, nullptr, nullptr, gi + SML_OFF_F2W, 512, 64, (int)(2 * B), 512, 64, 512}};
+        rc = sml_launch_umma_gemm(w2t, 2, SML_A_KM_GELU, SML_B_KN, SML_EPI_ACCUM, 1, 64, st);
+    } else {
+        rc = sml_launch_sgemm(w2, 2, SML_A_KM, SML_B_KN_GELU, SML_EPI_ACCUM, st);
+    }
     if (rc) return rc;
     SmlGemmProb w1[2] = {
         {w.dZ1, w.A, nullptr, nullptr, gu + SML_OFF_F1W, 512, 320, (int)B, 512, 320, 320},
         {w.dZ1 + B * 512, w.A + B * 320, nullptr, nullptr, gi + SML_OFF_F1W, 512, 320, (int)(2 * B), 512, 320, 320}};
-    rc = sml_launch_sgemm(w1, 2, SML_A_KM, SML_B_KN, SML_EPI_ACCUM, st);
+    rc = gemm(w1, 2, SML_A_KM, SML_B_KN, SML_EPI_ACCUM, 64, st);
     if (rc) return rc;
     SmlColsumProb cs[4] = {{w.dY, gu + SML_OFF_F2B, (int)B, 64, 64},
                            {w.dY + B * 64, gi + SML_OFF_F2B, (int)(2 * B), 64, 64},
@@ -154,10 +169,10 @@ int sml_transfer_fwd(const float *x_t, const float *x_hat, const int64_t *ids, i
         rc = sml_launch_conv_fwd(&g, 1, variant, A, nullptr, st);
         if (rc) return rc;
         SmlGemmProb fc1 = {A, theta_net + SML_OFF_F1W, theta_net + SML_OFF_F1B, nullptr, Z1, (int)n, 512, 320, 320, 320, 512};
-        rc = sml_launch_sgemm(&fc1, 1, SML_A_MK, SML_B_NK, SML_EPI_BIAS, st);
+        rc = gemm(&fc1, 1, SML_A_MK, SML_B_NK, SML_EPI_BIAS, 128, st);
         if (rc) return rc;
         SmlGemmProb fc2 = {Z1, theta_net + SML_OFF_F2W, theta_net + SML_OFF_F2B, nullptr, out + r0 * SML_D, (int)n, 64, 512, 512, 512, 64};
-        rc = sml_launch_sgemm(&fc2, 1, SML_A_MK_GELU, SML_B_NK, SML_EPI_BIAS, st);
+        rc = gemm(&fc2, 1, SML_A_MK_GELU, SML_B_NK, SML_EPI_BIAS, 64, st);
         if (rc) return rc;
     }
     if (normalize_out) return sml_launch_row_normalize(out, n_rows, st);
@@ -238,6 +253,40 @@ int sml_run_mf_grads(const sml_step_args *a, float *d_rows, float *scores, void 
     float *gu = a->g_theta, *gi = a->g_theta ? a->g_theta + SML_NET_STRIDE : nullptr;
     SmlConvBwdGroup bg[3] = {{g[0], nullptr, gu}, {g[1], nullptr, gi}, {g[2], nullptr, gi}};
     return sml_launch_conv_bwd(bg, 3, a->variant, w.dA, 0.f, d_rows, st);
+}
+
+int sml_debug_gemm(const float *A, const float *B, const float *bias, const float *aux, float *C, int M, int N, int K, int lda,
+                   int ldb, int ldc, int a_mode, int b_mode, int epi, int transpose_out, int bn, int tensor_cores, void *stream) {
+    int rc = sml_check_device();
+    if (rc) return rc;
+    SmlGemmProb p = {A, B, bias, aux, C, M, N, K, lda, ldb, ldc};
+    if (tensor_cores) return sml_launch_umma_gemm(&p, 1, a_mode, b_mode, epi, transpose_out, bn, (cudaStream_t)stream);
+    SML_REQUIRE(!transpose_out, SML_E_BADARG, "sml_debug_gemm: the SIMT kernel has no transposed store");
+    return sml_launch_sgemm(&p, 1, a_mode, b_mode, epi, (cudaStream_t)stream);
+}
+
+int sml_mf_epoch(const sml_step_args *a, int64_t n_total, void *stream) {
+    SML_REQUIRE(a && n_total >= 0, SML_E_BADARG, "sml_mf_epoch: bad arguments");
+    sml_step_args s = *a;
+    for (int64_t off = 0; off < n_total; off += a->batch) {
+        s.user = a->user + off; s.item = a->item + off; s.neg = a->neg + off;
+        s.batch = (n_total - off) < a->batch ? (n_total - off) : a->batch;
+        int rc = sml_mf_step(&s, stream);
+        if (rc) return rc;
+    }
+    return SML_OK;
+}
+
+int sml_tr_epoch(const sml_step_args *a, int64_t n_total, void *stream) {
+    SML_REQUIRE(a && n_total >= 0, SML_E_BADARG, "sml_tr_epoch: bad arguments");
+    sml_step_args s = *a;
+    for (int64_t off = 0; off < n_total; off += a->batch) {
+        s.user = a->user + off; s.item = a->item + off; s.neg = a->neg + off;
+        s.batch = (n_total - off) < a->batch ? (n_total - off) : a->batch;
+        int rc = sml_tr_step(&s, stream);
+        if (rc) return rc;
+    }
+    return SML_OK;
 }
 
 }  // extern "C"

@@ -23,18 +23,21 @@ class DeviceTestSet(object):
         self.rows = rows.contiguous()
         self.batch = batch
         self.emulate_reference_rng = emulate_reference_rng
-        self._rank_cache = None          # (table versions, gt, eq): K = 20/10/5 share one scoring pass
+        self.frozen = False              # set by callers that KNOW the tables do not change between calls
+        self._rank_cache = None          # (gt, eq) of the last scoring pass, reused only while frozen
 
     def __len__(self):
         return self.rows.shape[0]
 
     def ranks(self, model):
+        """One scoring pass.  The kernels update the tables through raw pointers, so tensor version
+        counters cannot detect changes: the pass is only reused (K = 20 / 10 / 5 of the real test,
+        model/transfer.py:855-868) while the caller holds ``frozen``."""
+        if self.frozen and self._rank_cache is not None:
+            return self._rank_cache
         uw, iw = model.user_laten.weight.data, model.item_laten.weight.data
-        key = (uw.data_ptr(), uw._version, iw.data_ptr(), iw._version)
-        if self._rank_cache is None or self._rank_cache[0] != key:
-            gt, eq = ops.eval_candidates(uw, iw, self.rows)
-            self._rank_cache = (key, gt, eq)
-        return self._rank_cache[1], self._rank_cache[2]
+        self._rank_cache = ops.eval_candidates(uw, iw, self.rows)
+        return self._rank_cache
 
 
 def test_model(model, test_set, old_user=None, old_item=None, topK=10, need_pbar=False):

@@ -26,6 +26,7 @@ import numpy as np
 import torch
 
 from .. import ops
+from ..profiling import EventTimers
 from ..data.batching import ReferenceStream, mf_epoch_triples, tr_epoch_triples
 from ..data.dataset import offlineDataset_withsample as SampleDaset
 from ..data.dataset2 import trainDataset_withPreSample as PreSampleDatast
@@ -169,6 +170,8 @@ class meta_train(object):
         self._loss = torch.zeros(2, dtype=torch.float32, device=self.device)
         self._ws = {}
         self._dev_cache = {}
+        self.dev_cache_cap = 6                     # period files kept resident on the device
+        self.events = EventTimers(False)           # CUDA-event phase timers (bench.py switches them on)
 
         self.recall = []
         self.ndcg = []
@@ -200,7 +203,7 @@ class meta_train(object):
         if hit is not None and hit[0] is arr:
             return hit[1]
         t = torch.from_numpy(np.ascontiguousarray(arr)).to(self.device, dtype=torch.int64, non_blocking=False)
-        if len(self._dev_cache) > 6:
+        if len(self._dev_cache) > self.dev_cache_cap:
             self._dev_cache.pop(next(iter(self._dev_cache)))
         self._dev_cache[key] = (arr, t)
         return t
@@ -222,11 +225,13 @@ class meta_train(object):
         return u, i, j
 
     def _upload(self, arrs):
-        return [torch.from_numpy(np.ascontiguousarray(x, dtype=np.int64)).to(self.device) for x in arrs]
+        return [x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.int64)).to(self.device)
+                for x in arrs]
 
     def _eval(self, test_set, topK):
         t0 = time.perf_counter()
-        r = test_model(self.MFbase, test_set, topK=topK)
+        with self.events("eval"):
+            r = test_model(self.MFbase, test_set, topK=topK)
         self.timers["eval"] += time.perf_counter() - t0
         return r
 
@@ -255,7 +260,8 @@ class meta_train(object):
             self.transfer.eval()
             t0 = time.perf_counter()
             triples = self._triples("MF", set_t_ds, stage_id, epoch, len(set_t_ds))
-            loss_all = self._mf_epoch(args, triples) / args.MF_batch_size       # :514-515
+            with self.events("mf_epoch"):
+                loss_all = self._mf_epoch(args, triples) / args.MF_batch_size       # :514-515
             self.timers["mf"] += time.perf_counter() - t0
             if val is not None:
                 recall, ndcg = self._eval(val, args.topK)
@@ -280,18 +286,15 @@ class meta_train(object):
         ws = self._workspace(B)
         n = user.numel()
         self._loss.zero_()
-        nb = 0
+        nb = -(-n // B)
         lr = self.MF_optimizer.param_groups[0]["lr"]
-        for s in range(0, n, B):
-            e = min(s + B, n)
-            a = ops.make_step_args(user=user[s:e], item=item[s:e], neg=neg[s:e],
-                                   last_user=self.last_user_weight, last_item=self.last_item_weight,
-                                   hat_user=uw, hat_item=iw, theta=self.transfer.theta, variant=self.transfer.variant,
-                                   loss=ops.LOSS_BCE if self.transfer.variant == ops.VARIANT_COM else ops.LOSS_BPR,
-                                   adam_state=self.MF_optimizer.adam_state, lr=lr, l2=args.l2, loss_out=self._loss,
-                                   workspace=ws, **self._mf)
-            ops.mf_step(a)
-            nb += 1
+        a = ops.make_step_args(user=user, item=item, neg=neg, batch=B,
+                               last_user=self.last_user_weight, last_item=self.last_item_weight,
+                               hat_user=uw, hat_item=iw, theta=self.transfer.theta, variant=self.transfer.variant,
+                               loss=ops.LOSS_BCE if self.transfer.variant == ops.VARIANT_COM else ops.LOSS_BPR,
+                               adam_state=self.MF_optimizer.adam_state, lr=lr, l2=args.l2, loss_out=self._loss,
+                               workspace=ws, **self._mf)
+        ops.mf_epoch(a, n)
         return self._loss[1].item() / nb
 
     # ------------------------------------------------------------------ transfer (outer) training
@@ -324,7 +327,8 @@ class meta_train(object):
             self.transfer.train()
             t0 = time.perf_counter()
             triples = self._triples("TR", set_tt_ds, stage_id, epoch, len(set_tt_ds))
-            loss_all = self._tr_epoch(args, triples)
+            with self.events("tr_epoch"):
+                loss_all = self._tr_epoch(args, triples)
             self.timers["tr"] += time.perf_counter() - t0
             print("one epcohs TR time cost:", time.time() - s_time)
             if self.need_writer:
@@ -349,20 +353,17 @@ class meta_train(object):
         ws = self._workspace(B)
         n = user.numel()
         self._loss.zero_()
-        nb = 0
+        nb = -(-n // B)
         g = self.transfer_optimizer.param_groups[0]
-        for s in range(0, n, B):
-            e = min(s + B, n)
-            a = ops.make_step_args(user=user[s:e], item=item[s:e], neg=neg[s:e],
-                                   last_user=self.last_user_weight, last_item=self.last_item_weight,
-                                   hat_user=self.user_weight_hat, hat_item=self.item_weight_hat,
-                                   theta=self.transfer.theta, variant=self.transfer.variant,
-                                   loss=ops.LOSS_BCE if self.transfer.variant == ops.VARIANT_COM else ops.LOSS_BPR,
-                                   adam_state=self.transfer_optimizer.adam_state, lr=g["lr"], l2=g["weight_decay"],
-                                   g_theta=self.transfer.theta_grad, m_theta=self._tr["m"], v_theta=self._tr["v"],
-                                   loss_out=self._loss, workspace=ws)
-            ops.tr_step(a)
-            nb += 1
+        a = ops.make_step_args(user=user, item=item, neg=neg, batch=B,
+                               last_user=self.last_user_weight, last_item=self.last_item_weight,
+                               hat_user=self.user_weight_hat, hat_item=self.item_weight_hat,
+                               theta=self.transfer.theta, variant=self.transfer.variant,
+                               loss=ops.LOSS_BCE if self.transfer.variant == ops.VARIANT_COM else ops.LOSS_BPR,
+                               adam_state=self.transfer_optimizer.adam_state, lr=g["lr"], l2=g["weight_decay"],
+                               g_theta=self.transfer.theta_grad, m_theta=self._tr["m"], v_theta=self._tr["v"],
+                               loss_out=self._loss, workspace=ws)
+        ops.tr_epoch(a, n)
         return self._loss[1].item() / nb
 
     # ------------------------------------------------------------------ one period
@@ -370,6 +371,7 @@ class meta_train(object):
         """The three test_model calls at K = 20, 10, 5 (model/transfer.py:810-823,855-868)."""
         self.test_num.append(now_test_arr.shape[0])
         now_test = self._test_set(now_test_arr)
+        now_test.frozen = True                      # three K on unchanged tables: one scoring pass
         for K, rl, nl, tag in ((20, self.recall, self.ndcg, ""), (10, self.recall_10, self.ndcg_10, " @10"),
                                (5, self.recall_5, self.ndcg_5, " @5")):
             recall, ndcg = self._eval(now_test, K)
@@ -431,10 +433,11 @@ class meta_train(object):
             raise TypeError("No such type transfer!!!")
         th = self.transfer.theta
         nu = self.transfer.variant == ops.VARIANT_CONV
-        ops.transfer_forward(self.last_user_weight, self.user_weight_hat, th[:ops.NET_STRIDE], variant=self.transfer.variant,
-                             normalize_out=nu, out=self.MFbase.user_laten.weight.data)
-        ops.transfer_forward(self.last_item_weight, self.item_weight_hat, th[ops.NET_STRIDE:], variant=self.transfer.variant,
-                             out=self.MFbase.item_laten.weight.data)
+        with self.events("updata"):
+            ops.transfer_forward(self.last_user_weight, self.user_weight_hat, th[:ops.NET_STRIDE], variant=self.transfer.variant,
+                                 normalize_out=nu, out=self.MFbase.user_laten.weight.data)
+            ops.transfer_forward(self.last_item_weight, self.item_weight_hat, th[ops.NET_STRIDE:], variant=self.transfer.variant,
+                                 out=self.MFbase.item_laten.weight.data)
         self.timers["updata"] += time.perf_counter() - t0
 
     def save_MF_weight(self, save_as="last"):

@@ -113,9 +113,9 @@ def step_workspace(batch, device, tag="step"):
 
 def make_step_args(*, user, item, neg, last_user, last_item, hat_user, hat_item, theta, variant=VARIANT_COM, loss=LOSS_BCE,
                    g_user=None, g_item=None, m_user=None, v_user=None, m_item=None, v_item=None, adam_state=None,
-                   lr=0.0, l2=0.0, g_theta=None, m_theta=None, v_theta=None, loss_out=None, workspace=None):
+                   lr=0.0, l2=0.0, g_theta=None, m_theta=None, v_theta=None, loss_out=None, workspace=None, batch=None):
     a = StepArgs()
-    B = user.numel()
+    B = user.numel() if batch is None else int(batch)
     a.user, a.item, a.neg, a.batch = ptr(_i64(user, "user")), ptr(_i64(item, "item")), ptr(_i64(neg, "neg")), B
     a.last_user, a.last_item = ptr(_f32(last_user, "last_user")), ptr(_f32(last_item, "last_item"))
     a.hat_user, a.hat_item = ptr(_f32(hat_user, "hat_user")), ptr(_f32(hat_item, "hat_item"))
@@ -140,6 +140,15 @@ def mf_step(args):
 
 def tr_step(args):
     check(lib().sml_tr_step(C.byref(args), stream()), "tr_step")
+
+
+def mf_epoch(args, n_total):
+    """args.user/item/neg point at n_total triples; args.batch is the nominal batch size."""
+    check(lib().sml_mf_epoch(C.byref(args), n_total, stream()), "mf_epoch")
+
+
+def tr_epoch(args, n_total):
+    check(lib().sml_tr_epoch(C.byref(args), n_total, stream()), "tr_epoch")
 
 
 def run_mf_grads(args, d_rows=None, scores=None):

@@ -24,6 +24,11 @@ def sample(a):
     return a[::5, ::7] if a.ndim == 2 and a.size > 20000 else a
 
 
-def rel_err(a, b):
+def rel_err(a, b, atol=1e-6):
+    """max |a-b| relative to max |b|; differences below ``atol`` count as zero (quantities that are
+    exactly 0 in the reference, e.g. the BPR fc2.bias gradient, come out as ~1e-8 rounding noise)."""
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
-    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+    d = float(np.abs(a - b).max())
+    if d < atol:
+        return 0.0
+    return d / max(float(np.abs(b).max()), 1e-30)

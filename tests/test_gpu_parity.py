@@ -268,5 +268,31 @@ def test_plain_mf_vs_oracle(dev):
     pn, mn, vn = ut.copy(), np.zeros_like(ut), np.zeros_like(ut)
     O.adam_step(pn, gu, mn, vn, 1, 0.01)
     assert np.abs(p.cpu().numpy() - pn).max() < 1e-5 and float(g_u.abs().max()) == 0.0
-EOF
-echo done
+
+
+def test_eval_sees_kernel_updates(dev):
+    """The step kernels write the tables through raw pointers (no tensor version bump): a test set
+    evaluated before and after a training step must not return a stale scoring pass."""
+    from sml_b200 import ops
+    from sml_b200.model.MF import MFbasemode
+    from sml_b200.evalution.evaluation2 import DeviceTestSet, test_model
+    rng = np.random.default_rng(2)
+    with torch.random.fork_rng(devices=[]):
+        mf = MFbasemode(64, 128, 64).to(dev)
+    rows = T(np.concatenate([rng.integers(0, 64, (200, 1)), rng.integers(0, 128, (200, 50))], 1).astype(np.int64), dev)
+    ts = DeviceTestSet(rows)
+    r0, n0 = test_model(mf, ts, topK=5)
+    uw, iw = mf.user_laten.weight.data, mf.item_laten.weight.data
+    g_u, g_i = torch.zeros_like(uw), torch.zeros_like(iw)
+    loss = torch.zeros(2, device=dev)
+    u = rows[:, 0].contiguous(); i = rows[:, 1].contiguous(); j = rows[:, 2].contiguous()
+    st = ops.new_adam_state(dev)
+    for _ in range(30):
+        ops.plain_mf_grads(uw, iw, u, i, j, g_u, g_i, loss)
+        ops.adam_tick(st, 0.05)
+        ops.adam_dense(uw, torch.zeros_like(uw), torch.zeros_like(uw), g_u, st)
+        ops.adam_dense(iw, torch.zeros_like(iw), torch.zeros_like(iw), g_i, st)
+    r1, n1 = test_model(mf, ts, topK=5)
+    r2, n2 = test_model(mf, DeviceTestSet(rows), topK=5)
+    assert r1 == r2 and float(n1) == float(n2)
+    assert r1 > r0                                   # training on the positives must move them up

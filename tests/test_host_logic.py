@@ -43,26 +43,28 @@ class HostProbe(meta_train):
 
     def _require_device(self, device):
         self.device = torch.device("cpu")
-        self.events = []
+        self.rec = []
 
     def _test_set(self, arr):
-        return arr
+        class _Arr(object):
+            shape = arr.shape
+        return _Arr()
 
     def _eval(self, test_set, topK):
         ReferenceStream.loader_iter()
-        self.events.append(("eval", test_set.shape[0], topK))
+        self.rec.append(("eval", test_set.shape[0], topK))
         return 0.0, torch.tensor(0.0)
 
     def _mf_epoch(self, args, triples):
-        self.events.append(("MF", np.stack(triples, 1)))
+        self.rec.append(("MF", np.stack(triples, 1)))
         return 0.0
 
     def _tr_epoch(self, args, triples):
-        self.events.append(("TR", np.stack(triples, 1)))
+        self.rec.append(("TR", np.stack(triples, 1)))
         return 0.0
 
     def updata(self):
-        self.events.append(("updata",))
+        self.rec.append(("updata",))
 
 
 @pytest.mark.parametrize("name,stop", [("period_run", False), ("period_run_stop", True)])
@@ -77,7 +79,7 @@ def test_batch_stream_matches_reference(golden, tmp_path, name, stop):
     probe = HostProbe(args, ds, U, I, 64)
     probe.run(args)
     kinds = [str(k) for k in g["log_kinds"]]
-    got = [e for e in probe.events if e[0] in ("MF", "TR")]
+    got = [e for e in probe.rec if e[0] in ("MF", "TR")]
     # one reference dataset instance may span several epochs (MF_epochs = 2 in the stop branch)
     ref = []
     for n, kind in enumerate(kinds):
@@ -89,7 +91,7 @@ def test_batch_stream_matches_reference(golden, tmp_path, name, stop):
     for (k, a), (_, b) in zip(got, ref):
         assert np.array_equal(a, b), k                               # sampled indices: bit-exact
     assert len(probe.test_num) == 3 and probe.test_num == [96, 96, 96]
-    n_updata = sum(1 for e in probe.events if e[0] == "updata")
+    n_updata = sum(1 for e in probe.rec if e[0] == "updata")
     assert n_updata > 0
 
 
