@@ -178,6 +178,14 @@ int sml_tr_epoch(const sml_step_args *args, int64_t n_total, void *stream);
  * term) if non-null and accumulates theta gradients into args->g_theta if non-null. */
 int sml_run_mf_grads(const sml_step_args *args, float *d_rows, float *scores /* [2B] s+, s- or null */, void *stream);
 
+/* ---- host helper (all pointers are HOST pointers) ------------------------------------------
+ * The sequential walk of offlineDataset_withsample's rejection sampler (data/dataset.py:62-71): sample s
+ * takes item_all[draws[p]] for successive p until (users[s], item) is not an interaction of the period
+ * (keys = sorted user*span+item).  Returns the number of draws consumed, or -1 if n_draws was too few. */
+int64_t sml_host_rejection_walk(const int64_t *draws_host, int64_t n_draws, const int64_t *users_host, int64_t n,
+                                const int64_t *item_all_host, const int64_t *keys_host, int64_t n_keys, int64_t span,
+                                int64_t *neg_host);
+
 /* ---- GEMM building block (exposed for tests and profiling) ---------------------------------
  * C[M,N] = epi(opA(A) opB(B)) with the fc-layer GEMM kernels the steps use.  a_mode: 0 A[m][k], 1 same
  * with GELU applied on load, 2 A[k][m], 3 A[k][m] + GELU.  b_mode: 0 B[n][k], 1 B[k][n], 2 B[k][n] + GELU.

@@ -55,6 +55,7 @@ _PROTOS = {
     "sml_mf_epoch": (_i32, [C.POINTER(StepArgs), _i64, _vp]),
     "sml_tr_epoch": (_i32, [C.POINTER(StepArgs), _i64, _vp]),
     "sml_run_mf_grads": (_i32, [C.POINTER(StepArgs), _vp, _vp, _vp]),
+    "sml_host_rejection_walk": (_i64, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
     "sml_debug_gemm": (_i32, [_vp, _vp, _vp, _vp, _vp] + [_i32] * 12 + [_vp]),
     "sml_plain_mf_grads": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }

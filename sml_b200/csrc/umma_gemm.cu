@@ -8,16 +8,17 @@
 // dropped lo*lo term is <= 2^-22 relative per product, so results agree with an fp32 FFMA GEMM to
 // ~1e-6 relative (tests/test_gpu_umma.py), inside the 1e-5 forward tolerance of the parity tests.
 //
-// Structure (one CTA = one 128 x BN output tile, 128 threads):
+// Structure (one CTA = one 128 x BN output tile, 256 threads):
 //   * operands are NOT moved by TMA: they need an elementwise transform (split, optional GELU) and,
-//     for weight gradients, a transpose, so the four warps load fp32 from global memory (coalesced
+//     for weight gradients, a transpose, so the eight warps load fp32 from global memory (coalesced
 //     128-bit or 32-bit accesses), transform in registers and write 16-byte vectors into shared memory
 //     in the canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices).  LBO = 144 B and
 //     SBO = 1152 B (instead of the dense 128 / 1024) skew the core matrices so that both store patterns
 //     are bank-conflict free;
-//   * a 3-stage ring of {A_hi, A_lo, B_hi, B_lo} K-chunks (32 fp32 of K each); one elected thread
-//     issues 12 tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) per chunk and commits them to the stage's
-//     mbarrier, which the producers wait on before overwriting the stage;
+//   * a 3-stage ring of {A_hi, A_lo, B_hi, B_lo} K-chunks (32 fp32 of K each) fed by 8 producer warps
+//     from a register double buffer (two chunks of global loads in flight per thread); producers signal
+//     full[s]; a ninth warp (one thread) waits on it, issues 12 tcgen05.mma.kind::tf32 (M=128, N=BN,
+//     K=8) per chunk and commits them to empty[s], which the producers wait on before reusing the stage;
 //   * the 128 x BN fp32 accumulator lives in TMEM (BN columns); the epilogue reads it back with
 //     tcgen05.ld (one row per thread), stages it through shared memory and writes coalesced rows with
 //     the fused epilogue (bias / multiply by GELU'(aux) / accumulate / transposed store).
@@ -27,7 +28,8 @@
 
 namespace {
 
-constexpr int UM_THREADS = 128;
+constexpr int UM_THREADS = 256;            // 8 producer/epilogue warps: two per scheduler, enough ILP/TLP for the operand transform
+constexpr int UM_CTA_THREADS = UM_THREADS + 32;   // + 1 warp that only issues tcgen05.mma
 constexpr int UM_BM = 128;
 constexpr int UM_BK = 32;                  // fp32 elements of K per stage
 constexpr int UM_STAGES = 3;
@@ -42,6 +44,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t ok;
@@ -54,10 +59,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!ok);
 }
 
+// round-to-nearest (ties away) to the 10-bit TF32 mantissa with two full-rate integer ops; cvt.rna.tf32.f32
+// gives the same bits for finite values but issues on the quarter-rate conversion pipe
 __device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 // 64-bit shared-memory matrix descriptor: K-major, SWIZZLE_NONE (layout_type 0), version 1 (sm_100)
@@ -96,15 +101,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 template <int ROWS> struct TileBytes { static constexpr uint32_t v = (ROWS / 8) * UM_SBO; };
 
 // ---- operand staging ---------------------------------------------------------------------------
-// K-contiguous source G[x][k] (pitch ld): 8 lanes cover one row's 128 B; each thread owns ROWS/16 (row, 16 B) pieces
+// K-contiguous source G[x][k] (pitch ld): 8 lanes cover one row's 128 B; each thread owns ROWS/32 (row, 16 B) pieces
 template <int ROWS, bool GELU>
 struct LoadKContig {
-    float4 v[ROWS / 16];
+    static constexpr int RSTEP = UM_THREADS / 8;       // rows covered by one pass of the CTA
+    static constexpr int NP = ROWS / RSTEP;
+    float4 v[NP];
     __device__ __forceinline__ void load(const float *__restrict__ G, int ld, int x0, int X, int k0, int K) {
         const int kq = threadIdx.x & 7, xr0 = threadIdx.x >> 3;
 #pragma unroll
-        for (int j = 0; j < ROWS / 16; ++j) {
-            const int x = x0 + xr0 + 16 * j, k = k0 + 4 * kq;
+        for (int j = 0; j < NP; ++j) {
+            const int x = x0 + xr0 + RSTEP * j, k = k0 + 4 * kq;
             float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
             if (x < X) {
                 const float *src = G + (size_t)x * ld + k;
@@ -117,8 +124,8 @@ struct LoadKContig {
     __device__ __forceinline__ void store(uint8_t *hi, uint8_t *lo) const {
         const int kq = threadIdx.x & 7, xr0 = threadIdx.x >> 3;
 #pragma unroll
-        for (int j = 0; j < ROWS / 16; ++j) {
-            const int xr = xr0 + 16 * j;
+        for (int j = 0; j < NP; ++j) {
+            const int xr = xr0 + RSTEP * j;
             float4 t = v[j];
             if (GELU) { t.x = sml_gelu(t.x); t.y = sml_gelu(t.y); t.z = sml_gelu(t.z); t.w = sml_gelu(t.w); }
             const float4 h = make_float4(tf32_rna(t.x), tf32_rna(t.y), tf32_rna(t.z), tf32_rna(t.w));
@@ -134,7 +141,7 @@ struct LoadKContig {
 // (coalesced 4-byte loads across the warp) and UM_BK * ROWS / 128 consecutive k, i.e. whole 16-byte K-quads
 template <int ROWS, bool GELU>
 struct LoadXContig {
-    static constexpr int KPT = UM_BK * ROWS / UM_THREADS;   // k per thread: 32 (ROWS=128) or 16 (ROWS=64)
+    static constexpr int KPT = UM_BK * ROWS / UM_THREADS;   // k per thread: 16 (ROWS=128) or 8 (ROWS=64)
     float v[KPT];
     __device__ __forceinline__ void load(const float *__restrict__ G, int ld, int x0, int X, int k0, int K) {
         const int xr = threadIdx.x % ROWS, kb = (threadIdx.x / ROWS) * KPT;
@@ -173,22 +180,27 @@ template <int BN> struct Smem {
 
 // A_KCONTIG: A source is [m][k]; else [k][m].   B_KCONTIG: B source is [n][k]; else [k][n].
 template <int BN, bool A_KCONTIG, bool A_GELU, bool B_KCONTIG, bool B_GELU, int EPI>
-__global__ void __launch_bounds__(UM_THREADS, 1)
+__global__ void __launch_bounds__(UM_CTA_THREADS, 1)
 k_umma_gemm(UmmaParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     using S = Smem<BN>;
     const SmlGemmProb p = P.p[blockIdx.z];
     const int m0 = blockIdx.y * UM_BM, n0 = blockIdx.x * BN;
     if (m0 >= p.M || n0 >= p.N) return;                       // whole CTA exits: nothing allocated yet
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + S::TOTAL - 64);   // [UM_STAGES] stage-free + [1] accumulator-ready
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::TOTAL - 16);
+    // mbarriers: full[s] (256 producer arrivals), empty[s] (1 tcgen05.commit), done (1 commit)
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + S::TOTAL - 64);
+    uint64_t *empty = full + UM_STAGES;
+    uint64_t *done = empty + UM_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::TOTAL - 8);
     const int warp = threadIdx.x >> 5;
+    constexpr int MMA_WARP = UM_THREADS / 32;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i <= UM_STAGES; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < UM_STAGES; ++i) { mbar_init(&full[i], UM_THREADS); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -199,58 +211,88 @@ k_umma_gemm(UmmaParams P) {
 
     // instruction descriptor: D=f32 (bit 4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at 17, M>>4 at 24
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
-
-    typename std::conditional<A_KCONTIG, LoadKContig<UM_BM, A_GELU>, LoadXContig<UM_BM, A_GELU>>::type la;
-    typename std::conditional<B_KCONTIG, LoadKContig<BN, B_GELU>, LoadXContig<BN, B_GELU>>::type lb;
-
     const int nchunks = (p.K + UM_BK - 1) / UM_BK;
-    la.load(p.A, p.lda, m0, p.M, 0, p.K);
-    lb.load(p.B, p.ldb, n0, p.N, 0, p.K);
-    for (int c = 0; c < nchunks; ++c) {
-        const int s = c % UM_STAGES;
-        uint8_t *st = smem + s * S::STAGE;
-        if (c >= UM_STAGES) mbar_wait(&bars[s], ((c / UM_STAGES) - 1) & 1);     // MMAs that read this stage are done
-        la.store(st, st + S::A_BYTES);
-        lb.store(st + 2 * S::A_BYTES, st + 2 * S::A_BYTES + S::B_BYTES);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");             // generic-proxy writes -> async proxy (UMMA)
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi = smem_u32(st), a_lo = a_hi + S::A_BYTES, b_hi = a_hi + 2 * S::A_BYTES, b_lo = b_hi + S::B_BYTES;
+
+    if (warp == MMA_WARP) {
+        // ===== MMA issuer: one thread; waits for a full stage, issues its 12 MMAs, commits to empty[s] =====
+        if ((threadIdx.x & 31) == 0) {
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % UM_STAGES;
+                mbar_wait(&full[s], (c / UM_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi = smem_u32(smem + s * S::STAGE), a_lo = a_hi + S::A_BYTES, b_hi = a_hi + 2 * S::A_BYTES,
+                               b_lo = b_hi + S::B_BYTES;
 #pragma unroll
-            for (int k = 0; k < UM_BK / 8; ++k) {
-                const uint32_t ko = k * 2 * UM_LBO;                              // one MMA = K 8 = two core matrices
-                const uint64_t ah = make_desc(a_hi + ko), al = make_desc(a_lo + ko), bh = make_desc(b_hi + ko), bl = make_desc(b_lo + ko);
-                umma_tf32(tmem, al, bh, IDESC, (c | k) != 0);                    // small terms first
-                umma_tf32(tmem, ah, bl, IDESC, 1);
-                umma_tf32(tmem, ah, bh, IDESC, 1);
+                for (int k = 0; k < UM_BK / 8; ++k) {
+                    const uint32_t ko = k * 2 * UM_LBO;                          // one MMA = K 8 = two core matrices
+                    const uint64_t ah = make_desc(a_hi + ko), al = make_desc(a_lo + ko), bh = make_desc(b_hi + ko), bl = make_desc(b_lo + ko);
+                    umma_tf32(tmem, al, bh, IDESC, (c | k) != 0);                // small terms first
+                    umma_tf32(tmem, ah, bl, IDESC, 1);
+                    umma_tf32(tmem, ah, bh, IDESC, 1);
+                }
+                umma_commit(&empty[s]);                                          // stage reusable once these MMAs retire
             }
-            umma_commit(&bars[s]);
-            if (c == nchunks - 1) umma_commit(&bars[UM_STAGES]);
+            umma_commit(done);
         }
-        if (c + 1 < nchunks) {                                                   // overlaps with the MMAs just issued
-            la.load(p.A, p.lda, m0, p.M, (c + 1) * UM_BK, p.K);
-            lb.load(p.B, p.ldb, n0, p.N, (c + 1) * UM_BK, p.K);
+        __syncwarp();
+    } else {
+        // ===== producers: global fp32 -> registers (two chunks in flight) -> hi/lo split -> canonical smem =====
+        using LA = typename std::conditional<A_KCONTIG, LoadKContig<UM_BM, A_GELU>, LoadXContig<UM_BM, A_GELU>>::type;
+        using LB = typename std::conditional<B_KCONTIG, LoadKContig<BN, B_GELU>, LoadXContig<BN, B_GELU>>::type;
+        LA la0, la1;
+        LB lb0, lb1;
+        auto put = [&](int c, const LA &la, const LB &lb) {
+            const int s = c % UM_STAGES;
+            uint8_t *st = smem + s * S::STAGE;
+            if (c >= UM_STAGES) mbar_wait(&empty[s], ((c / UM_STAGES) - 1) & 1); // the MMAs that read this stage are done
+            la.store(st, st + S::A_BYTES);
+            lb.store(st + 2 * S::A_BYTES, st + 2 * S::A_BYTES + S::B_BYTES);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // generic-proxy writes -> async proxy (UMMA)
+            mbar_arrive(&full[s]);
+        };
+        la0.load(p.A, p.lda, m0, p.M, 0, p.K);
+        lb0.load(p.B, p.ldb, n0, p.N, 0, p.K);
+        if (nchunks > 1) {
+            la1.load(p.A, p.lda, m0, p.M, UM_BK, p.K);
+            lb1.load(p.B, p.ldb, n0, p.N, UM_BK, p.K);
+        }
+        for (int c = 0; c < nchunks; c += 2) {
+            put(c, la0, lb0);
+            if (c + 2 < nchunks) {
+                la0.load(p.A, p.lda, m0, p.M, (c + 2) * UM_BK, p.K);
+                lb0.load(p.B, p.ldb, n0, p.N, (c + 2) * UM_BK, p.K);
+            }
+            if (c + 1 < nchunks) {
+                put(c + 1, la1, lb1);
+                if (c + 3 < nchunks) {
+                    la1.load(p.A, p.lda, m0, p.M, (c + 3) * UM_BK, p.K);
+                    lb1.load(p.B, p.ldb, n0, p.N, (c + 3) * UM_BK, p.K);
+                }
+            }
         }
     }
     // ---- epilogue ----
-    mbar_wait(&bars[UM_STAGES], 0);
+    mbar_wait(done, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float *epi = reinterpret_cast<float *>(smem);                                // [128][BN+1], aliases the stages (all MMAs done)
-    const int row = threadIdx.x;                                                 // TMEM lane == accumulator row
+    if (warp < MMA_WARP) {
+    // TMEM lane == accumulator row; warp w may only touch lanes [32*(w%4), +32): warps w and w+4 share a
+    // lane quarter and split the columns
+    const int row = (warp & 3) * 32 + (threadIdx.x & 31);
 #pragma unroll
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = (warp >> 2) * (BN / 2); c0 < (warp >> 2) * (BN / 2) + BN / 2; c0 += 32) {
         float v[32];
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) epi[row * (BN + 1) + c0 + i] = v[i];
     }
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN) : "memory");
+    if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN) : "memory");
     if (!P.transpose_out) {
         // coalesced rows: a warp writes 32 consecutive n of one m
-        for (int idx = threadIdx.x; idx < UM_BM * BN; idx += UM_THREADS) {
+        for (int idx = threadIdx.x; idx < UM_BM * BN; idx += UM_CTA_THREADS) {
             const int r = idx / BN, cc = idx % BN;
             const int m = m0 + r, n = n0 + cc;
             if (m < p.M && n < p.N) {
@@ -264,7 +306,7 @@ k_umma_gemm(UmmaParams P) {
         }
     } else {
         // C is stored [n][m] (pitch ldc): a warp writes 32 consecutive m of one n
-        for (int idx = threadIdx.x; idx < UM_BM * BN; idx += UM_THREADS) {
+        for (int idx = threadIdx.x; idx < UM_BM * BN; idx += UM_CTA_THREADS) {
             const int cc = idx / UM_BM, r = idx % UM_BM;
             const int m = m0 + r, n = n0 + cc;
             if (m < p.M && n < p.N) {
@@ -285,7 +327,7 @@ int launch_one(const UmmaParams &P, dim3 grid, cudaStream_t st) {
         SML_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<BN>::TOTAL));
         attr_set = true;
     }
-    kern<<<grid, UM_THREADS, Smem<BN>::TOTAL, st>>>(P);
+    kern<<<grid, UM_CTA_THREADS, Smem<BN>::TOTAL, st>>>(P);
     SML_LAUNCH_OK();
     return SML_OK;
 }

@@ -43,39 +43,29 @@ class ReferenceStream(object):
     @staticmethod
     def alone_negatives(ds: offlineDataset_withsample, order):
         """Sequential rejection sampling in sampler order, vectorised between rejections."""
+        from .._lib import lib
         n = len(order)
-        users = ds.user[order]
-        P = len(ds.item_all)
+        users = np.ascontiguousarray(ds.user[order], dtype=np.int64)
+        item_all = np.ascontiguousarray(ds.item_all, dtype=np.int64)
+        keys = np.ascontiguousarray(ds._keys, dtype=np.int64)
+        P = len(item_all)
         state = np.random.get_state()
-        margin = max(64, n // 8)
+        margin = max(64, n // 4)
+        neg = np.empty(n, dtype=np.int64)
+        walk = lib().sml_host_rejection_walk
         while True:
-            draws = np.random.randint(0, P, size=n + margin)
-            neg = np.empty(n, dtype=ds.item_all.dtype)
-            s = 0          # next sample
-            p = 0          # next draw
-            ok = True
-            while s < n:
-                m = min(n - s, len(draws) - p)
-                if m <= 0:
-                    ok = False
-                    break
-                cand = ds.item_all[draws[p:p + m]]
-                rej = ds.interacted(users[s:s + m], cand)
-                k = int(np.argmax(rej)) if rej.any() else m
-                neg[s:s + k] = cand[:k]
-                s += k
-                p += k
-                if k < m:
-                    p += 1        # the rejected draw is consumed; sample s retries with the next draw
-            if ok:
+            draws = np.ascontiguousarray(np.random.randint(0, P, size=n + margin), dtype=np.int64)
+            p = walk(draws.ctypes.data, len(draws), users.ctypes.data, n, item_all.ctypes.data, keys.ctypes.data, len(keys),
+                     ds._span, neg.ctypes.data)
+            if p >= 0:
                 break
             np.random.set_state(state)
-            margin *= 2
+            margin *= 4
         # leave the global generator exactly where the reference would: p draws consumed
         np.random.set_state(state)
         if p:
             np.random.randint(0, P, size=p)
-        return neg
+        return neg.astype(ds.item_all.dtype, copy=False)
 
 
 def mf_epoch_triples(ds: trainDataset_withPreSample, order):

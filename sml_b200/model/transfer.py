@@ -208,6 +208,14 @@ class meta_train(object):
         self._dev_cache[key] = (arr, t)
         return t
 
+    def _sample_dataset(self, arr):
+        """SampleDaset(set_tt) is stateless (its draws come from the global numpy generator), so the
+        per-period user->items index is built once per file instead of once per outer phase."""
+        hit = getattr(self, "_tt_ds", None)
+        if hit is None or hit[0] is not arr:
+            self._tt_ds = (arr, SampleDaset(arr))
+        return self._tt_ds[1]
+
     def _test_set(self, arr):
         return DeviceTestSet(self._to_device(arr), emulate_reference_rng=self.emulate_reference_rng)
 
@@ -304,7 +312,7 @@ class meta_train(object):
         self.MFbase.eval()
         now_test = None
         if self.TR_train_sampleTYpe == "alone":
-            set_tt_ds = SampleDaset(set_tt)
+            set_tt_ds = self._sample_dataset(set_tt)
             compute_performance = False
             if val is not None:
                 now_test = self._test_set(val)
