@@ -160,6 +160,10 @@ typedef struct {
 } sml_step_args;
 
 size_t sml_step_workspace_bytes(int64_t batch);
+/* Row layout of the per-step matrices (and of d_rows in sml_run_mf_grads): user rows at [0, batch),
+ * positive-item rows at [*row_pos, +batch), negative-item rows at [*row_neg, +batch); returns the total
+ * (128-padded) row count. */
+int64_t sml_step_rows(int64_t batch, int64_t *row_pos_host, int64_t *row_neg_host);
 /* HOT LOOP A body, model/transfer.py:463-511: gather -> transfer fwd (3 nets calls) -> BCE
  * -> + l2*0.5*sum(w_hat^2) -> row gradients through the x_hat channel -> scatter-add ->
  * dense Adam on both latent tables.  theta is read-only here. */
@@ -174,8 +178,9 @@ int sml_tr_step(const sml_step_args *args, void *stream);
 int sml_mf_epoch(const sml_step_args *args, int64_t n_total, void *stream);
 int sml_tr_epoch(const sml_step_args *args, int64_t n_total, void *stream);
 /* Forward + loss + gradients without any optimizer update (ConvTransfer_com.run_MF +
- * backward, model/conv_transfer.py:113-135): writes d_rows [3B,64] = dL/d x_hat rows (no l2
- * term) if non-null and accumulates theta gradients into args->g_theta if non-null. */
+ * backward, model/conv_transfer.py:113-135): writes d_rows [sml_step_rows(B), 64] = dL/d x_hat rows (no l2
+ * term; row layout of sml_step_rows) if non-null and accumulates theta gradients into args->g_theta if
+ * non-null. */
 int sml_run_mf_grads(const sml_step_args *args, float *d_rows, float *scores /* [2B] s+, s- or null */, void *stream);
 
 /* ---- host helper (all pointers are HOST pointers) ------------------------------------------

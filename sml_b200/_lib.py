@@ -50,6 +50,7 @@ _PROTOS = {
     "sml_adam_tick": (_i32, [_vp, _dbl, _dbl, _dbl, _vp]),
     "sml_adam_dense": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _vp]),
     "sml_step_workspace_bytes": (_sz, [_i64]),
+    "sml_step_rows": (_i64, [_i64, C.POINTER(_i64), C.POINTER(_i64)]),
     "sml_mf_step": (_i32, [C.POINTER(StepArgs), _vp]),
     "sml_tr_step": (_i32, [C.POINTER(StepArgs), _vp]),
     "sml_mf_epoch": (_i32, [C.POINTER(StepArgs), _i64, _vp]),

@@ -13,6 +13,7 @@
 // One warp owns one row; lane l owns latent dims l and l+32, so every global access is a
 // coalesced 128 B line and the row norm is one shuffle tree.
 #include "sml_common.cuh"
+#include "umma_pack.cuh"
 
 namespace {
 
@@ -65,7 +66,7 @@ __device__ __forceinline__ void conv_point(const ConvW &w, float x0, float x1, f
 // ---------------------------------------------------------------------------------------------
 template <int R>
 __global__ void __launch_bounds__(CONV_THREADS)
-k_conv_fwd(ConvParams P, float *__restrict__ A, float *__restrict__ rowsq) {
+k_conv_fwd(ConvParams P, float *__restrict__ A, uint8_t *__restrict__ Apk, float *__restrict__ rowsq) {
     __shared__ ConvW sw;
     const int gi = blockIdx.y;
     const SmlRowGroup g = P.g[gi];
@@ -90,13 +91,18 @@ k_conv_fwd(ConvParams P, float *__restrict__ A, float *__restrict__ rowsq) {
             const float q = warp_sum(x1[0] * x1[0] + x1[1] * x1[1]);
             if (lane == 0) rowsq[g.row0 + r] = q;
         }
-        float *a = A + (g.row0 + r) * SML_FC1_IN;
+        float *a = A ? A + (g.row0 + r) * SML_FC1_IN : nullptr;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             float z1[10], h1[10], z2[5];
             conv_point<R>(sw, x0[h], x1[h], x2[h], z1, h1, z2);
 #pragma unroll
-            for (int m = 0; m < 5; ++m) a[m * SML_D + lane + 32 * h] = sml_gelu(z2[m]);
+            for (int m = 0; m < 5; ++m) {
+                const float v = sml_gelu(z2[m]);
+                const int k = m * SML_D + lane + 32 * h;          // channel-major flatten (conv_transfer.py:43)
+                if (a) a[k] = v;
+                if (Apk) pk_store1(Apk, 128, SML_FC1_IN / PK_BK, g.row0 + r, k, v);
+            }
         }
     }
 }
@@ -230,16 +236,16 @@ constexpr int LOSS_THREADS = 256;
 constexpr int LOSS_WARPS = LOSS_THREADS / 32;
 
 __global__ void __launch_bounds__(LOSS_THREADS)
-k_loss(const float *__restrict__ Y, const float *__restrict__ rowsq, int64_t B, int loss_kind, int normalize_user,
-       float l2, float *__restrict__ dY, float *__restrict__ scores, float *__restrict__ loss_out,
-       float *__restrict__ partials, unsigned int *__restrict__ ticket) {
+k_loss(const float *__restrict__ Y, const float *__restrict__ rowsq, int64_t B, int64_t rowP, int64_t rowN, int loss_kind,
+       int normalize_user, float l2, float *__restrict__ dY, uint8_t *__restrict__ dYpk, float *__restrict__ scores,
+       float *__restrict__ loss_out, float *__restrict__ partials, unsigned int *__restrict__ ticket) {
     __shared__ float s_part[LOSS_WARPS][3];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float acc_pos = 0.f, acc_neg = 0.f, acc_sq = 0.f;   // lane 0 only
     const float invB = 1.0f / (float)B;
     for (int64_t b = (int64_t)blockIdx.x * LOSS_WARPS + w; b < B; b += (int64_t)gridDim.x * LOSS_WARPS) {
-        const float *yu = Y + b * SML_D, *yi = Y + (B + b) * SML_D, *yj = Y + (2 * B + b) * SML_D;
+        const float *yu = Y + b * SML_D, *yi = Y + (rowP + b) * SML_D, *yj = Y + (rowN + b) * SML_D;
         float u[2] = {yu[lane], yu[lane + 32]};
         const float i_[2] = {yi[lane], yi[lane + 32]};
         const float j_[2] = {yj[lane], yj[lane + 32]};
@@ -265,15 +271,21 @@ k_loss(const float *__restrict__ Y, const float *__restrict__ rowsq, int64_t B, 
             dsp = -sml_sigmoid(-x);
             dsn = -dsp;
         }
-        if (rowsq && lane == 0) acc_sq += rowsq[b] + rowsq[B + b] + rowsq[2 * B + b];
+        if (rowsq && lane == 0) acc_sq += rowsq[b] + rowsq[rowP + b] + rowsq[rowN + b];
         if (scores && lane == 0) { scores[b] = sp; scores[B + b] = sn; }
         if (dY) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int k = lane + 32 * h;
-                dY[b * SML_D + k] = (dsp * i_[h] + dsn * j_[h]) * inv_n;
-                dY[(B + b) * SML_D + k] = dsp * u[h];
-                dY[(2 * B + b) * SML_D + k] = dsn * u[h];
+                const float du = (dsp * i_[h] + dsn * j_[h]) * inv_n, di = dsp * u[h], dj = dsn * u[h];
+                dY[b * SML_D + k] = du;
+                dY[(rowP + b) * SML_D + k] = di;
+                dY[(rowN + b) * SML_D + k] = dj;
+                if (dYpk) {
+                    pk_store1(dYpk, 128, SML_D / PK_BK, b, k, du);
+                    pk_store1(dYpk, 128, SML_D / PK_BK, rowP + b, k, di);
+                    pk_store1(dYpk, 128, SML_D / PK_BK, rowN + b, k, dj);
+                }
             }
         }
     }
@@ -325,7 +337,8 @@ int grid_for_rows(int64_t max_n) {
 
 }  // namespace
 
-int sml_launch_conv_fwd(const SmlRowGroup *groups, int n_groups, int variant, float *A, float *rowsq, cudaStream_t st) {
+int sml_launch_conv_fwd(const SmlRowGroup *groups, int n_groups, int variant, float *A, uint8_t *Apk, float *rowsq,
+                        cudaStream_t st) {
     SML_REQUIRE(n_groups >= 1 && n_groups <= MAX_GROUPS, SML_E_BADARG, "conv_fwd: bad group count %d", n_groups);
     ConvParams P;
     P.n_groups = n_groups;
@@ -333,8 +346,8 @@ int sml_launch_conv_fwd(const SmlRowGroup *groups, int n_groups, int variant, fl
     for (int i = 0; i < n_groups; ++i) { P.g[i] = groups[i]; if (groups[i].n > max_n) max_n = groups[i].n; }
     if (max_n == 0) return SML_OK;
     dim3 grid(grid_for_rows(max_n), n_groups);
-    if (variant == SML_VARIANT_COM) k_conv_fwd<3><<<grid, CONV_THREADS, 0, st>>>(P, A, rowsq);
-    else k_conv_fwd<2><<<grid, CONV_THREADS, 0, st>>>(P, A, rowsq);
+    if (variant == SML_VARIANT_COM) k_conv_fwd<3><<<grid, CONV_THREADS, 0, st>>>(P, A, Apk, rowsq);
+    else k_conv_fwd<2><<<grid, CONV_THREADS, 0, st>>>(P, A, Apk, rowsq);
     SML_LAUNCH_OK();
     return SML_OK;
 }
@@ -371,13 +384,13 @@ int sml_launch_conv_bwd(const SmlConvBwdGroup *groups, int n_groups, int variant
     return SML_OK;
 }
 
-int sml_launch_loss(const float *Y, const float *rowsq, int64_t B, int loss_kind, int normalize_user, float l2,
-                    float *dY, float *scores, float *loss_out, float *partials, unsigned int *ticket,
-                    cudaStream_t st) {
+int sml_launch_loss(const float *Y, const float *rowsq, int64_t B, int64_t row_pos, int64_t row_neg, int loss_kind,
+                    int normalize_user, float l2, float *dY, uint8_t *dYpk, float *scores, float *loss_out, float *partials,
+                    unsigned int *ticket, cudaStream_t st) {
     int64_t blocks = (B + LOSS_WARPS - 1) / LOSS_WARPS;
     if (blocks > 1024) blocks = 1024;   // partials[] holds 3 * 1024 floats
-    k_loss<<<(int)blocks, LOSS_THREADS, 0, st>>>(Y, rowsq, B, loss_kind, normalize_user, l2, dY, scores, loss_out,
-                                                 partials, ticket);
+    k_loss<<<(int)blocks, LOSS_THREADS, 0, st>>>(Y, rowsq, B, row_pos, row_neg, loss_kind, normalize_user, l2, dY, dYpk, scores,
+                                                 loss_out, partials, ticket);
     SML_LAUNCH_OK();
     return SML_OK;
 }

@@ -39,11 +39,23 @@ void sml_note_launch();   // bumps the kernel-launch counter read by sml_launch_
         }                                                                                        \
     } while (0)
 
-// x * sigmoid(1.702 x)  (model/conv_transfer.py:9-10).  expf (not __expf): fp32-accurate.
+// sigmoid for the loss (accurate expf + IEEE division)
 __device__ __forceinline__ float sml_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
-__device__ __forceinline__ float sml_gelu(float x) { return x * sml_sigmoid(SML_GELU_ALPHA * x); }
+// GELU(x) = x * sigmoid(1.702 x)  (model/conv_transfer.py:9-10) and its derivative.  The transfer network
+// evaluates 15 of these per (row, latent dim) in the conv stage and 512 per row after fc1, so they use
+// the two SFU approximations ex2.approx and rcp.approx (relative error ~2^-22 each) instead of expf + IEEE
+// division: ~8 instructions instead of ~28.  Measured end-to-end effect on the forward: < 1e-6 relative
+// (tests/test_gpu_parity.py tolerances are 1e-5).
+__device__ __forceinline__ float sml_sig1702(float x) {
+    // 1 / (1 + 2^(-1.702 * log2(e) * x))
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-2.4554669595930157f * x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+}
+__device__ __forceinline__ float sml_gelu(float x) { return x * sml_sig1702(x); }
 __device__ __forceinline__ float sml_gelu_grad(float x) {
-    float s = sml_sigmoid(SML_GELU_ALPHA * x);
+    const float s = sml_sig1702(x);
     return s + x * SML_GELU_ALPHA * s * (1.0f - s);
 }
 
@@ -67,8 +79,10 @@ struct SmlRowGroup {
     int64_t row0;        // first row of the group in the packed [N, .] workspace matrices
 };
 
-// conv prologue: A[N,320] (fc1 input) for every row of the groups; rowsq[n] = sum x_hat^2 (or null)
-int sml_launch_conv_fwd(const SmlRowGroup *groups, int n_groups, int variant, float *A, float *rowsq, cudaStream_t st);
+// conv prologue: fc1 input for every row of the groups, as plain A[N,320] (or null) and/or as a packed
+// tensor-core operand Apk (umma_pack.cuh, 128-row tiles, or null); rowsq[n] = sum x_hat^2 (or null)
+int sml_launch_conv_fwd(const SmlRowGroup *groups, int n_groups, int variant, float *A, uint8_t *Apk, float *rowsq,
+                        cudaStream_t st);
 
 // conv backward.  dA [N,320].  mode 0: scatter (dx_hat + l2*x_hat) into g_tab rows (atomic);
 // mode 1: write dx_hat to d_rows [N,64];  theta_grad != null: accumulate conv1/conv2 grads.
@@ -100,9 +114,37 @@ int sml_use_tensor_cores();
 struct SmlColsumProb { const float *X; float *out; int rows, cols, ld; };
 int sml_launch_colsum(const SmlColsumProb *probs, int n_probs, cudaStream_t st);
 
-// loss + dY
-int sml_launch_loss(const float *Y, const float *rowsq, int64_t B, int loss_kind, int normalize_user, float l2,
-                    float *dY, float *scores, float *loss_out, float *partials, unsigned int *ticket,
-                    cudaStream_t st);
+// loss + dY.  Rows of Y / dY / rowsq: user b at b, positive item at row_pos + b, negative at row_neg + b.
+// dYpk (optional): dY additionally as a packed tensor-core operand (K = 64).
+int sml_launch_loss(const float *Y, const float *rowsq, int64_t B, int64_t row_pos, int64_t row_neg, int loss_kind,
+                    int normalize_user, float l2, float *dY, uint8_t *dYpk, float *scores, float *loss_out, float *partials,
+                    unsigned int *ticket, cudaStream_t st);
+
+// tcgen05 GEMM with pre-packed operands (umma_packed.cu)
+enum { SML_PK_FC1 = 0, SML_PK_FC2 = 1, SML_PK_D2 = 2, SML_PK_D1 = 3 };
+struct SmlPkProb {
+    const uint8_t *A;     // packed A, 128-row tiles
+    const uint8_t *B;     // packed B (weights), BN-row tiles
+    int KC;               // K / 32
+    int m_tiles;          // row tiles of this problem
+    int a_tile0;          // first tile of this problem inside A
+    int64_t row0;         // plain row of the first tile
+    int M;                // valid rows (plain stores are guarded)
+    int N;                // output columns
+    const float *bias;    // [N] (fc1 / fc2)
+    const float *aux;     // plain [rows][ldc] pre-activations for the GELU' epilogue (d2)
+    float *C;             // plain output [rows][ldc] or null
+    int ldc;
+    uint8_t *Cpk;         // packed output = A operand of the next GEMM (K = N), or null
+    int c_tile0;
+};
+int sml_launch_umma_packed(const SmlPkProb *probs, int n_probs, int epi, cudaStream_t st);
+// packed weight operands of the nets: per net SML_PK_THETA_BYTES
+constexpr size_t SML_PK_OFF_P1 = 0;            // W1   as B[512][320], 128-row blocks (fc1 forward)
+constexpr size_t SML_PK_OFF_P2 = 1474560;      // W2   as B[64][512],   64-row blocks (fc2 forward)
+constexpr size_t SML_PK_OFF_P3 = 1769472;      // W2^T as B[512][64],  128-row blocks (dZ1 = dY W2)
+constexpr size_t SML_PK_OFF_P4 = 2064384;      // W1^T as B[320][512],  64-row blocks (dA = dZ1 W1)
+constexpr size_t SML_PK_THETA_BYTES = 3538944;
+int sml_launch_pack_theta(const float *theta, uint8_t *out, int n_nets, cudaStream_t st);
 
 int sml_launch_row_normalize(float *Y, int64_t n, cudaStream_t st);

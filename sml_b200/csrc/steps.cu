@@ -1,43 +1,69 @@
 // Host-side sequencing of the kernels behind the step-level C ABI (no device code here).
 // Every function only enqueues work on the caller's stream: no allocation, no synchronisation,
 // so a whole step (and a whole epoch of steps) can be captured into one CUDA graph.
+//
+// Row layout of every per-step matrix (plain [rows, .] and packed 128-row tiles alike):
+//     user rows      [0, B)                     user net
+//     positive items [Bp, Bp + B)               item net      Bp = B rounded up to 128
+//     negative items [Bp + B, Bp + 2B)          item net
+// so that no 128-row tensor-core tile straddles the two nets and the item rows stay contiguous
+// (one K range for the item net's weight gradients).
 #include "sml_common.cuh"
+#include "umma_pack.cuh"
 
 namespace {
 
-constexpr int64_t FWD_CHUNK = 8192;   // rows per pass of the SIMT transfer forward
+constexpr int64_t FWD_CHUNK = 16384;   // rows per pass of the full-table transfer forward
 
-// fc GEMM dispatch: tcgen05 3xTF32 by default, SIMT fp32 when SML_GEMM=simt
-int gemm(const SmlGemmProb *probs, int n, int a_mode, int b_mode, int epi, int bn, cudaStream_t st) {
-    if (sml_use_tensor_cores()) return sml_launch_umma_gemm(probs, n, a_mode, b_mode, epi, 0, bn, st);
-    return sml_launch_sgemm(probs, n, a_mode, b_mode, epi, st);
+inline int64_t up128(int64_t x) { return (x + 127) / 128 * 128; }
+
+struct Rows {
+    int64_t B, Bp, R;          // batch, padded user segment, total padded rows
+    int user_tiles, item_tiles;
+};
+Rows rows_of(int64_t B) {
+    Rows r;
+    r.B = B; r.Bp = up128(B); r.R = r.Bp + up128(2 * B);
+    r.user_tiles = (int)(r.Bp / 128); r.item_tiles = (int)(up128(2 * B) / 128);
+    return r;
 }
 
 struct StepWs {
     unsigned int *ticket;   // [64] (only [0] used), re-armed by k_loss
     float *partials;        // [3 * 1024]
-    float *A, *Z1, *Y, *dY, *dZ1, *dA, *rowsq;
+    float *A, *Z1, *Y, *dY, *dZ1, *dA, *rowsq;          // plain, R rows
+    uint8_t *Apk, *Gpk, *dYpk, *dZpk;                   // packed operands (128-row tiles over the R rows)
+    uint8_t *theta_pk;                                  // packed weights, 2 nets
 };
 
 size_t step_ws_bytes(int64_t B) {
-    const size_t N = (size_t)3 * B;
-    return 256 + 3 * 1024 * sizeof(float) + N * (320 + 512 + 64 + 64 + 512 + 320 + 1) * sizeof(float) + 7 * 256;
+    const Rows r = rows_of(B);
+    const size_t R = (size_t)r.R, T = R / 128;
+    size_t n = 256 + 3 * 1024 * sizeof(float) + R * (320 + 512 + 64 + 64 + 512 + 320 + 1) * sizeof(float);
+    n += T * (size_t)(10 + 16 + 2 + 16) * pk_block_bytes(128) + 2 * SML_PK_THETA_BYTES;
+    return n + 16 * 256;
 }
 
 StepWs carve(void *ws, int64_t B) {
     StepWs w;
     char *p = (char *)ws;
-    auto take = [&](size_t bytes) { char *r = p; p += sml_align_up(bytes, 256); return r; };
-    const size_t N = (size_t)3 * B;
+    auto take = [&](size_t bytes) { char *q = p; p += sml_align_up(bytes, 256); return q; };
+    const Rows r = rows_of(B);
+    const size_t R = (size_t)r.R, T = R / 128;
     w.ticket = (unsigned int *)take(256);
     w.partials = (float *)take(3 * 1024 * sizeof(float));
-    w.A = (float *)take(N * 320 * sizeof(float));
-    w.Z1 = (float *)take(N * 512 * sizeof(float));
-    w.Y = (float *)take(N * 64 * sizeof(float));
-    w.dY = (float *)take(N * 64 * sizeof(float));
-    w.dZ1 = (float *)take(N * 512 * sizeof(float));
-    w.dA = (float *)take(N * 320 * sizeof(float));
-    w.rowsq = (float *)take(N * sizeof(float));
+    w.A = (float *)take(R * 320 * sizeof(float));
+    w.Z1 = (float *)take(R * 512 * sizeof(float));
+    w.Y = (float *)take(R * 64 * sizeof(float));
+    w.dY = (float *)take(R * 64 * sizeof(float));
+    w.dZ1 = (float *)take(R * 512 * sizeof(float));
+    w.dA = (float *)take(R * 320 * sizeof(float));
+    w.rowsq = (float *)take(R * sizeof(float));
+    w.Apk = (uint8_t *)take(T * 10 * pk_block_bytes(128));
+    w.Gpk = (uint8_t *)take(T * 16 * pk_block_bytes(128));
+    w.dYpk = (uint8_t *)take(T * 2 * pk_block_bytes(128));
+    w.dZpk = (uint8_t *)take(T * 16 * pk_block_bytes(128));
+    w.theta_pk = (uint8_t *)take(2 * SML_PK_THETA_BYTES);
     return w;
 }
 
@@ -57,140 +83,137 @@ int check_args(const sml_step_args *a, const char *who) {
 }
 
 void make_groups(const sml_step_args *a, SmlRowGroup g[3]) {
-    const int64_t B = a->batch;
+    const Rows r = rows_of(a->batch);
     const float *tu = a->theta, *ti = a->theta + SML_NET_STRIDE;
-    g[0] = SmlRowGroup{a->last_user, a->hat_user, a->user, tu, B, 0};
-    g[1] = SmlRowGroup{a->last_item, a->hat_item, a->item, ti, B, B};
-    g[2] = SmlRowGroup{a->last_item, a->hat_item, a->neg, ti, B, 2 * B};
+    g[0] = SmlRowGroup{a->last_user, a->hat_user, a->user, tu, r.B, 0};
+    g[1] = SmlRowGroup{a->last_item, a->hat_item, a->item, ti, r.B, r.Bp};
+    g[2] = SmlRowGroup{a->last_item, a->hat_item, a->neg, ti, r.B, r.Bp + r.B};
 }
 
-// forward through fc2 + loss + data gradients down to dZ1 (shared by all step flavours)
-int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, float l2, float *scores, cudaStream_t st) {
-    const int64_t B = a->batch;
+// two-net problem pair for the packed GEMMs
+void pk_pair(SmlPkProb out[2], const Rows &r, const uint8_t *A, int KC, size_t w_off, int N, const float *theta, size_t bias_off,
+             const float *aux, float *C, int ldc, uint8_t *Cpk, const uint8_t *theta_pk) {
+    for (int net = 0; net < 2; ++net) {
+        SmlPkProb &p = out[net];
+        p.A = A; p.B = theta_pk + net * SML_PK_THETA_BYTES + w_off; p.KC = KC;
+        p.m_tiles = net ? r.item_tiles : r.user_tiles;
+        p.a_tile0 = net ? r.user_tiles : 0;
+        p.row0 = net ? r.Bp : 0;
+        p.M = (int)(net ? 2 * r.B : r.B);
+        p.N = N;
+        p.bias = bias_off ? theta + (size_t)net * SML_NET_STRIDE + bias_off : nullptr;
+        p.aux = aux; p.C = C; p.ldc = ldc; p.Cpk = Cpk; p.c_tile0 = p.a_tile0;
+    }
+}
+
+// forward through fc2 + loss + data gradients down to dZ1 (shared by all step flavours).
+// need_plain_A: the transfer step's fc1 weight gradient reads A.
+int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, bool need_plain_A, bool pack_theta, float l2,
+                     float *scores, cudaStream_t st) {
+    const Rows r = rows_of(a->batch);
+    const int64_t B = r.B;
     const float *tu = a->theta, *ti = a->theta + SML_NET_STRIDE;
+    const bool tc = sml_use_tensor_cores() != 0;
     SmlRowGroup g[3];
     make_groups(a, g);
-    int rc = sml_launch_conv_fwd(g, 3, a->variant, w.A, want_rowsq ? w.rowsq : nullptr, st);
+    int rc;
+    if (tc && pack_theta) {
+        rc = sml_launch_pack_theta(a->theta, w.theta_pk, 2, st);
+        if (rc) return rc;
+    }
+    rc = sml_launch_conv_fwd(g, 3, a->variant, (!tc || need_plain_A) ? w.A : nullptr, tc ? w.Apk : nullptr,
+                             want_rowsq ? w.rowsq : nullptr, st);
     if (rc) return rc;
-    // fc1: Z1 = A W1^T + b1   (conv_transfer.py:47), user rows with the user net, item rows with the item net
-    SmlGemmProb fc1[2] = {
-        {w.A, tu + SML_OFF_F1W, tu + SML_OFF_F1B, nullptr, w.Z1, (int)B, 512, 320, 320, 320, 512},
-        {w.A + B * 320, ti + SML_OFF_F1W, ti + SML_OFF_F1B, nullptr, w.Z1 + B * 512, (int)(2 * B), 512, 320, 320, 320, 512}};
-    rc = gemm(fc1, 2, SML_A_MK, SML_B_NK, SML_EPI_BIAS, 128, st);
+    if (tc) {
+        SmlPkProb p[2];
+        // fc1: Z1 = A W1^T + b1 (conv_transfer.py:47); also emits GELU(Z1) packed for fc2
+        pk_pair(p, r, w.Apk, 10, SML_PK_OFF_P1, 512, a->theta, SML_OFF_F1B, nullptr, w.Z1, 512, w.Gpk, w.theta_pk);
+        rc = sml_launch_umma_packed(p, 2, SML_PK_FC1, st);
+        if (rc) return rc;
+        // fc2: Y = GELU(Z1) W2^T + b2 (:48-49)
+        pk_pair(p, r, w.Gpk, 16, SML_PK_OFF_P2, 64, a->theta, SML_OFF_F2B, nullptr, w.Y, 64, nullptr, w.theta_pk);
+        rc = sml_launch_umma_packed(p, 2, SML_PK_FC2, st);
+        if (rc) return rc;
+    } else {
+        SmlGemmProb fc1[2] = {
+            {w.A, tu + SML_OFF_F1W, tu + SML_OFF_F1B, nullptr, w.Z1, (int)B, 512, 320, 320, 320, 512},
+            {w.A + r.Bp * 320, ti + SML_OFF_F1W, ti + SML_OFF_F1B, nullptr, w.Z1 + r.Bp * 512, (int)(2 * B), 512, 320, 320, 320, 512}};
+        rc = sml_launch_sgemm(fc1, 2, SML_A_MK, SML_B_NK, SML_EPI_BIAS, st);
+        if (rc) return rc;
+        SmlGemmProb fc2[2] = {
+            {w.Z1, tu + SML_OFF_F2W, tu + SML_OFF_F2B, nullptr, w.Y, (int)B, 64, 512, 512, 512, 64},
+            {w.Z1 + r.Bp * 512, ti + SML_OFF_F2W, ti + SML_OFF_F2B, nullptr, w.Y + r.Bp * 64, (int)(2 * B), 64, 512, 512, 512, 64}};
+        rc = sml_launch_sgemm(fc2, 2, SML_A_MK_GELU, SML_B_NK, SML_EPI_BIAS, st);
+        if (rc) return rc;
+    }
+    rc = sml_launch_loss(w.Y, want_rowsq ? w.rowsq : nullptr, B, r.Bp, r.Bp + B, a->loss, a->variant == SML_VARIANT_CONV, l2, w.dY,
+                         tc ? w.dYpk : nullptr, scores, a->loss_out, w.partials, w.ticket, st);
     if (rc) return rc;
-    // fc2: Y = g(Z1) W2^T + b2   (:48-49)
-    SmlGemmProb fc2[2] = {
-        {w.Z1, tu + SML_OFF_F2W, tu + SML_OFF_F2B, nullptr, w.Y, (int)B, 64, 512, 512, 512, 64},
-        {w.Z1 + B * 512, ti + SML_OFF_F2W, ti + SML_OFF_F2B, nullptr, w.Y + B * 64, (int)(2 * B), 64, 512, 512, 512, 64}};
-    rc = gemm(fc2, 2, SML_A_MK_GELU, SML_B_NK, SML_EPI_BIAS, 64, st);
-    if (rc) return rc;
-    rc = sml_launch_loss(w.Y, want_rowsq ? w.rowsq : nullptr, B, a->loss, a->variant == SML_VARIANT_CONV, l2, w.dY, scores,
-                         a->loss_out, w.partials, w.ticket, st);
-    if (rc) return rc;
-    // dZ1 = (dY W2) * g'(Z1)
+    // dZ1 = (dY W2) * GELU'(Z1)
+    if (tc) {
+        SmlPkProb p[2];
+        pk_pair(p, r, w.dYpk, 2, SML_PK_OFF_P3, 512, a->theta, 0, w.Z1, w.dZ1, 512, w.dZpk, w.theta_pk);
+        return sml_launch_umma_packed(p, 2, SML_PK_D2, st);
+    }
     SmlGemmProb d2[2] = {
         {w.dY, tu + SML_OFF_F2W, nullptr, w.Z1, w.dZ1, (int)B, 512, 64, 64, 512, 512},
-        {w.dY + B * 64, ti + SML_OFF_F2W, nullptr, w.Z1 + B * 512, w.dZ1 + B * 512, (int)(2 * B), 512, 64, 64, 512, 512}};
-    return gemm(d2, 2, SML_A_MK, SML_B_KN, SML_EPI_MUL_GELU_GRAD, 128, st);
+        {w.dY + r.Bp * 64, ti + SML_OFF_F2W, nullptr, w.Z1 + r.Bp * 512, w.dZ1 + r.Bp * 512, (int)(2 * B), 512, 64, 64, 512, 512}};
+    return sml_launch_sgemm(d2, 2, SML_A_MK, SML_B_KN, SML_EPI_MUL_GELU_GRAD, st);
 }
 
 int fc1_dgrad(const sml_step_args *a, const StepWs &w, cudaStream_t st) {
-    const int64_t B = a->batch;
+    const Rows r = rows_of(a->batch);
+    const int64_t B = r.B;
+    if (sml_use_tensor_cores()) {
+        SmlPkProb p[2];
+        pk_pair(p, r, w.dZpk, 16, SML_PK_OFF_P4, 320, a->theta, 0, nullptr, w.dA, 320, nullptr, w.theta_pk);
+        return sml_launch_umma_packed(p, 2, SML_PK_D1, st);
+    }
     const float *tu = a->theta, *ti = a->theta + SML_NET_STRIDE;
     SmlGemmProb d1[2] = {
         {w.dZ1, tu + SML_OFF_F1W, nullptr, nullptr, w.dA, (int)B, 320, 512, 512, 320, 320},
-        {w.dZ1 + B * 512, ti + SML_OFF_F1W, nullptr, nullptr, w.dA + B * 320, (int)(2 * B), 320, 512, 512, 320, 320}};
-    return gemm(d1, 2, SML_A_MK, SML_B_KN, SML_EPI_NONE, 64, st);
+        {w.dZ1 + r.Bp * 512, ti + SML_OFF_F1W, nullptr, nullptr, w.dA + r.Bp * 320, (int)(2 * B), 320, 512, 512, 320, 320}};
+    return sml_launch_sgemm(d1, 2, SML_A_MK, SML_B_KN, SML_EPI_NONE, st);
 }
 
 // fc1/fc2 weight + bias gradients accumulated into g_theta  (theta grads of conv_transfer.py:47-49)
 int fc_wgrads(const sml_step_args *a, const StepWs &w, float *g_theta, cudaStream_t st) {
-    const int64_t B = a->batch;
+    const Rows r = rows_of(a->batch);
+    const int64_t B = r.B, Bp = r.Bp;
     float *gu = g_theta, *gi = g_theta + SML_NET_STRIDE;
-    SmlGemmProb w2[2] = {
-        {w.dY, w.Z1, nullptr, nullptr, gu + SML_OFF_F2W, 64, 512, (int)B, 64, 512, 512},
-        {w.dY + B * 64, w.Z1 + B * 512, nullptr, nullptr, gi + SML_OFF_F2W, 64, 512, (int)(2 * B), 64, 512, 512}};
     int rc;
     if (sml_use_tensor_cores()) {
         // tensor-core tiles are 128 rows tall: compute dW2^T [512, 64] = g(Z1)^T dY and store it transposed
         SmlGemmProb w2t[2] = {
             {w.Z1, w.dY, nullptr, nullptr, gu + SML_OFF_F2W, 512, 64, (int)B, 512, 64, 512},
-            {w.Z1 + B * 512, w.dY + B * 64, nullptr, nullptr, gi + SML_OFF_F2W, 512, 64, (int)(2 * B), 512, 64, 512}};
+            {w.Z1 + Bp * 512, w.dY + Bp * 64, nullptr, nullptr, gi + SML_OFF_F2W, 512, 64, (int)(2 * B), 512, 64, 512}};
         rc = sml_launch_umma_gemm(w2t, 2, SML_A_KM_GELU, SML_B_KN, SML_EPI_ACCUM, 1, 64, st);
     } else {
+        SmlGemmProb w2[2] = {
+            {w.dY, w.Z1, nullptr, nullptr, gu + SML_OFF_F2W, 64, 512, (int)B, 64, 512, 512},
+            {w.dY + Bp * 64, w.Z1 + Bp * 512, nullptr, nullptr, gi + SML_OFF_F2W, 64, 512, (int)(2 * B), 64, 512, 512}};
         rc = sml_launch_sgemm(w2, 2, SML_A_KM, SML_B_KN_GELU, SML_EPI_ACCUM, st);
     }
     if (rc) return rc;
     SmlGemmProb w1[2] = {
         {w.dZ1, w.A, nullptr, nullptr, gu + SML_OFF_F1W, 512, 320, (int)B, 512, 320, 320},
-        {w.dZ1 + B * 512, w.A + B * 320, nullptr, nullptr, gi + SML_OFF_F1W, 512, 320, (int)(2 * B), 512, 320, 320}};
-    rc = gemm(w1, 2, SML_A_KM, SML_B_KN, SML_EPI_ACCUM, 64, st);
+        {w.dZ1 + Bp * 512, w.A + Bp * 320, nullptr, nullptr, gi + SML_OFF_F1W, 512, 320, (int)(2 * B), 512, 320, 320}};
+    if (sml_use_tensor_cores()) rc = sml_launch_umma_gemm(w1, 2, SML_A_KM, SML_B_KN, SML_EPI_ACCUM, 0, 64, st);
+    else rc = sml_launch_sgemm(w1, 2, SML_A_KM, SML_B_KN, SML_EPI_ACCUM, st);
     if (rc) return rc;
     SmlColsumProb cs[4] = {{w.dY, gu + SML_OFF_F2B, (int)B, 64, 64},
-                           {w.dY + B * 64, gi + SML_OFF_F2B, (int)(2 * B), 64, 64},
+                           {w.dY + Bp * 64, gi + SML_OFF_F2B, (int)(2 * B), 64, 64},
                            {w.dZ1, gu + SML_OFF_F1B, (int)B, 512, 512},
-                           {w.dZ1 + B * 512, gi + SML_OFF_F1B, (int)(2 * B), 512, 512}};
+                           {w.dZ1 + Bp * 512, gi + SML_OFF_F1B, (int)(2 * B), 512, 512}};
     return sml_launch_colsum(cs, 4, st);
 }
 
-}  // namespace
-
-extern "C" {
-
-size_t sml_step_workspace_bytes(int64_t batch) { return batch > 0 ? step_ws_bytes(batch) : 0; }
-
-size_t sml_transfer_fwd_workspace_bytes(int64_t n_rows) {
-    const int64_t ch = n_rows < FWD_CHUNK ? n_rows : FWD_CHUNK;
-    return ch > 0 ? (size_t)ch * (320 + 512) * sizeof(float) + 512 : 0;
-}
-
-int sml_transfer_fwd(const float *x_t, const float *x_hat, const int64_t *ids, int64_t n_rows, int d, int variant,
-                     const float *theta_net, int normalize_out, float *out, void *workspace, size_t workspace_bytes,
-                     void *stream) {
-    int rc = sml_check_device();
-    if (rc) return rc;
-    SML_REQUIRE(d == SML_D, SML_E_UNSUPPORTED, "sml_transfer_fwd: d=%d unsupported (d must be %d)", d, SML_D);
-    SML_REQUIRE(variant == SML_VARIANT_COM || variant == SML_VARIANT_CONV, SML_E_BADARG, "sml_transfer_fwd: bad variant %d", variant);
-    SML_REQUIRE(x_t && x_hat && theta_net && out, SML_E_BADARG, "sml_transfer_fwd: null pointer");
-    SML_REQUIRE(n_rows >= 0, SML_E_BADARG, "sml_transfer_fwd: negative n_rows");
-    if (n_rows == 0) return SML_OK;
-    SML_REQUIRE(workspace && workspace_bytes >= sml_transfer_fwd_workspace_bytes(n_rows), SML_E_WORKSPACE,
-                "sml_transfer_fwd: workspace too small (%zu < %zu bytes)", workspace_bytes,
-                sml_transfer_fwd_workspace_bytes(n_rows));
-    cudaStream_t st = (cudaStream_t)stream;
-    const int64_t ch = n_rows < FWD_CHUNK ? n_rows : FWD_CHUNK;
-    float *A = (float *)workspace;
-    float *Z1 = A + sml_align_up((size_t)ch * 320, 64);
-    for (int64_t r0 = 0; r0 < n_rows; r0 += ch) {
-        const int64_t n = (n_rows - r0) < ch ? (n_rows - r0) : ch;
-        SmlRowGroup g;
-        if (ids) g = SmlRowGroup{x_t, x_hat, ids + r0, theta_net, n, 0};
-        else g = SmlRowGroup{x_t + r0 * SML_D, x_hat + r0 * SML_D, nullptr, theta_net, n, 0};
-        rc = sml_launch_conv_fwd(&g, 1, variant, A, nullptr, st);
-        if (rc) return rc;
-        SmlGemmProb fc1 = {A, theta_net + SML_OFF_F1W, theta_net + SML_OFF_F1B, nullptr, Z1, (int)n, 512, 320, 320, 320, 512};
-        rc = gemm(&fc1, 1, SML_A_MK, SML_B_NK, SML_EPI_BIAS, 128, st);
-        if (rc) return rc;
-        SmlGemmProb fc2 = {Z1, theta_net + SML_OFF_F2W, theta_net + SML_OFF_F2B, nullptr, out + r0 * SML_D, (int)n, 64, 512, 512, 512, 64};
-        rc = gemm(&fc2, 1, SML_A_MK_GELU, SML_B_NK, SML_EPI_BIAS, 64, st);
-        if (rc) return rc;
-    }
-    if (normalize_out) return sml_launch_row_normalize(out, n_rows, st);
-    return SML_OK;
-}
-
-int sml_mf_step(const sml_step_args *a, void *stream) {
-    int rc = sml_check_device();
-    if (rc) return rc;
-    rc = check_args(a, "sml_mf_step");
-    if (rc) return rc;
-    SML_REQUIRE(a->g_user && a->g_item && a->m_user && a->v_user && a->m_item && a->v_item && a->adam_state, SML_E_BADARG,
-                "sml_mf_step: null gradient / Adam-state pointer");
+int mf_step_impl(const sml_step_args *a, bool pack_theta, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const StepWs w = carve(a->workspace, a->batch);
-    rc = sml_adam_tick(a->adam_state, a->lr, 0.9, 0.999, stream);
+    int rc = sml_adam_tick(a->adam_state, a->lr, 0.9, 0.999, stream);
     if (rc) return rc;
-    rc = forward_and_loss(a, w, true, (float)a->l2, nullptr, st);
+    rc = forward_and_loss(a, w, true, false, pack_theta, (float)a->l2, nullptr, st);
     if (rc) return rc;
     rc = fc1_dgrad(a, w, st);
     if (rc) return rc;
@@ -205,6 +228,96 @@ int sml_mf_step(const sml_step_args *a, void *stream) {
     return sml_adam_dense(a->hat_item, a->m_item, a->v_item, a->g_item, a->n_items * SML_D, a->adam_state, 0.9, 0.999, 1e-8, 0.0, 1, stream);
 }
 
+int check_mf(const sml_step_args *a) {
+    int rc = sml_check_device();
+    if (rc) return rc;
+    rc = check_args(a, "sml_mf_step");
+    if (rc) return rc;
+    SML_REQUIRE(a->g_user && a->g_item && a->m_user && a->v_user && a->m_item && a->v_item && a->adam_state, SML_E_BADARG,
+                "sml_mf_step: null gradient / Adam-state pointer");
+    return SML_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t sml_step_workspace_bytes(int64_t batch) { return batch > 0 ? step_ws_bytes(batch) : 0; }
+
+int64_t sml_step_rows(int64_t batch, int64_t *row_pos, int64_t *row_neg) {
+    const Rows r = rows_of(batch);
+    if (row_pos) *row_pos = r.Bp;
+    if (row_neg) *row_neg = r.Bp + r.B;
+    return r.R;
+}
+
+size_t sml_transfer_fwd_workspace_bytes(int64_t n_rows) {
+    const int64_t ch = up128(n_rows < FWD_CHUNK ? n_rows : FWD_CHUNK);
+    if (ch <= 0) return 0;
+    return (size_t)ch * (320 + 512) * sizeof(float) + (size_t)(ch / 128) * (10 + 16) * pk_block_bytes(128) + SML_PK_THETA_BYTES + 4096;
+}
+
+int sml_transfer_fwd(const float *x_t, const float *x_hat, const int64_t *ids, int64_t n_rows, int d, int variant,
+                     const float *theta_net, int normalize_out, float *out, void *workspace, size_t workspace_bytes,
+                     void *stream) {
+    int rc = sml_check_device();
+    if (rc) return rc;
+    SML_REQUIRE(d == SML_D, SML_E_UNSUPPORTED, "sml_transfer_fwd: d=%d unsupported (d must be %d)", d, SML_D);
+    SML_REQUIRE(variant == SML_VARIANT_COM || variant == SML_VARIANT_CONV, SML_E_BADARG, "sml_transfer_fwd: bad variant %d", variant);
+    SML_REQUIRE(n_rows >= 0, SML_E_BADARG, "sml_transfer_fwd: negative n_rows");
+    if (n_rows == 0) return SML_OK;
+    SML_REQUIRE(x_t && x_hat && theta_net && out, SML_E_BADARG, "sml_transfer_fwd: null pointer");
+    SML_REQUIRE(workspace && workspace_bytes >= sml_transfer_fwd_workspace_bytes(n_rows), SML_E_WORKSPACE,
+                "sml_transfer_fwd: workspace too small (%zu < %zu bytes)", workspace_bytes,
+                sml_transfer_fwd_workspace_bytes(n_rows));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool tc = sml_use_tensor_cores() != 0;
+    const int64_t ch = up128(n_rows < FWD_CHUNK ? n_rows : FWD_CHUNK);
+    char *p = (char *)workspace;
+    auto take = [&](size_t bytes) { char *q = p; p += sml_align_up(bytes, 256); return q; };
+    float *A = (float *)take((size_t)ch * 320 * sizeof(float));
+    float *Z1 = (float *)take((size_t)ch * 512 * sizeof(float));
+    uint8_t *Apk = (uint8_t *)take((size_t)(ch / 128) * 10 * pk_block_bytes(128));
+    uint8_t *Gpk = (uint8_t *)take((size_t)(ch / 128) * 16 * pk_block_bytes(128));
+    uint8_t *theta_pk = (uint8_t *)take(SML_PK_THETA_BYTES);
+    if (tc) {
+        rc = sml_launch_pack_theta(theta_net, theta_pk, 1, st);
+        if (rc) return rc;
+    }
+    for (int64_t r0 = 0; r0 < n_rows; r0 += ch) {
+        const int64_t n = (n_rows - r0) < ch ? (n_rows - r0) : ch;
+        SmlRowGroup g;
+        if (ids) g = SmlRowGroup{x_t, x_hat, ids + r0, theta_net, n, 0};
+        else g = SmlRowGroup{x_t + r0 * SML_D, x_hat + r0 * SML_D, nullptr, theta_net, n, 0};
+        rc = sml_launch_conv_fwd(&g, 1, variant, tc ? nullptr : A, tc ? Apk : nullptr, nullptr, st);
+        if (rc) return rc;
+        if (tc) {
+            const int tiles = (int)(up128(n) / 128);
+            SmlPkProb f1 = {Apk, theta_pk + SML_PK_OFF_P1, 10, tiles, 0, 0, (int)n, 512, theta_net + SML_OFF_F1B, nullptr, nullptr, 512, Gpk, 0};
+            rc = sml_launch_umma_packed(&f1, 1, SML_PK_FC1, st);
+            if (rc) return rc;
+            SmlPkProb f2 = {Gpk, theta_pk + SML_PK_OFF_P2, 16, tiles, 0, 0, (int)n, 64, theta_net + SML_OFF_F2B, nullptr, out + r0 * SML_D, 64, nullptr, 0};
+            rc = sml_launch_umma_packed(&f2, 1, SML_PK_FC2, st);
+            if (rc) return rc;
+        } else {
+            SmlGemmProb fc1 = {A, theta_net + SML_OFF_F1W, theta_net + SML_OFF_F1B, nullptr, Z1, (int)n, 512, 320, 320, 320, 512};
+            rc = sml_launch_sgemm(&fc1, 1, SML_A_MK, SML_B_NK, SML_EPI_BIAS, st);
+            if (rc) return rc;
+            SmlGemmProb fc2 = {Z1, theta_net + SML_OFF_F2W, theta_net + SML_OFF_F2B, nullptr, out + r0 * SML_D, (int)n, 64, 512, 512, 512, 64};
+            rc = sml_launch_sgemm(&fc2, 1, SML_A_MK_GELU, SML_B_NK, SML_EPI_BIAS, st);
+            if (rc) return rc;
+        }
+    }
+    if (normalize_out) return sml_launch_row_normalize(out, n_rows, st);
+    return SML_OK;
+}
+
+int sml_mf_step(const sml_step_args *a, void *stream) {
+    int rc = check_mf(a);
+    if (rc) return rc;
+    return mf_step_impl(a, true, stream);
+}
+
 int sml_tr_step(const sml_step_args *a, void *stream) {
     int rc = sml_check_device();
     if (rc) return rc;
@@ -215,7 +328,7 @@ int sml_tr_step(const sml_step_args *a, void *stream) {
     const StepWs w = carve(a->workspace, a->batch);
     rc = sml_adam_tick(a->adam_state, a->lr, 0.9, 0.999, stream);
     if (rc) return rc;
-    rc = forward_and_loss(a, w, false, 0.f, nullptr, st);
+    rc = forward_and_loss(a, w, false, true, true, 0.f, nullptr, st);      // theta changes every step: re-pack
     if (rc) return rc;
     rc = fc_wgrads(a, w, a->g_theta, st);
     if (rc) return rc;
@@ -239,7 +352,7 @@ int sml_run_mf_grads(const sml_step_args *a, float *d_rows, float *scores, void 
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const StepWs w = carve(a->workspace, a->batch);
-    rc = forward_and_loss(a, w, false, 0.f, scores, st);
+    rc = forward_and_loss(a, w, false, a->g_theta != nullptr, true, 0.f, scores, st);
     if (rc) return rc;
     if (a->g_theta) {
         rc = fc_wgrads(a, w, a->g_theta, st);
@@ -252,6 +365,7 @@ int sml_run_mf_grads(const sml_step_args *a, float *d_rows, float *scores, void 
     make_groups(a, g);
     float *gu = a->g_theta, *gi = a->g_theta ? a->g_theta + SML_NET_STRIDE : nullptr;
     SmlConvBwdGroup bg[3] = {{g[0], nullptr, gu}, {g[1], nullptr, gi}, {g[2], nullptr, gi}};
+    // d_rows uses the step row layout (sml_step_rows): user rows at 0, positives at row_pos, negatives at row_neg
     return sml_launch_conv_bwd(bg, 3, a->variant, w.dA, 0.f, d_rows, st);
 }
 
@@ -267,12 +381,18 @@ int sml_debug_gemm(const float *A, const float *B, const float *bias, const floa
 
 int sml_mf_epoch(const sml_step_args *a, int64_t n_total, void *stream) {
     SML_REQUIRE(a && n_total >= 0, SML_E_BADARG, "sml_mf_epoch: bad arguments");
+    int rc = check_mf(a);
+    if (rc) return rc;
     sml_step_args s = *a;
+    bool first = true;
     for (int64_t off = 0; off < n_total; off += a->batch) {
         s.user = a->user + off; s.item = a->item + off; s.neg = a->neg + off;
         s.batch = (n_total - off) < a->batch ? (n_total - off) : a->batch;
-        int rc = sml_mf_step(&s, stream);
+        // theta is frozen during the MF epoch (model/transfer.py:428,460): pack its tensor-core operands once.
+        // (the workspace carve depends on the batch size, so a short last batch re-packs into its own layout)
+        rc = mf_step_impl(&s, first || s.batch != a->batch, stream);
         if (rc) return rc;
+        first = false;
     }
     return SML_OK;
 }

@@ -59,10 +59,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!ok);
 }
 
-// round-to-nearest (ties away) to the 10-bit TF32 mantissa with two full-rate integer ops; cvt.rna.tf32.f32
-// gives the same bits for finite values but issues on the quarter-rate conversion pipe
+// round-to-nearest (ties away) to the 10-bit TF32 mantissa with full-rate integer ops (cvt.rna.tf32.f32 gives
+// the same bits for finite values but issues on the quarter-rate conversion pipe); NaN / Inf pass through
 __device__ __forceinline__ float tf32_rna(float x) {
-    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    const uint32_t b = __float_as_uint(x);
+    const uint32_t r = (b + 0x1000u) & 0xFFFFE000u;
+    return __uint_as_float((b & 0x7F800000u) == 0x7F800000u ? b : r);
 }
 
 // 64-bit shared-memory matrix descriptor: K-major, SWIZZLE_NONE (layout_type 0), version 1 (sm_100)

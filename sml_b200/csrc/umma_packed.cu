@@ -1,0 +1,290 @@
+// fp32-accurate GEMM on the tcgen05 tensor cores with PRE-PACKED operands (umma_pack.cuh): the four
+// GEMMs on the critical chain of every step and of the full-table transfer
+//     fc1:  Z1 = A W1^T + b1      (A from the conv prologue)         -> plain Z1 + packed GELU(Z1)
+//     fc2:  Y  = GELU(Z1) W2^T + b2                                   -> plain Y
+//     d2 :  dZ1 = (dY W2) * GELU'(Z1)                                 -> plain dZ1 + packed dZ1
+//     d1 :  dA  = dZ1 W1                                              -> plain dA
+// (model/conv_transfer.py:47-49 of the reference and their autograd).  The 3xTF32 split
+// (x = hi + lo, hi*hi + lo*hi + hi*lo accumulated in fp32 in TMEM) is done ONCE per element by whoever
+// produces the operand (conv kernel, loss kernel, the previous GEMM's epilogue, the theta packer), so
+// this kernel moves operands with one cp.async.bulk per 36 KB block and spends no instructions on them.
+//
+// One CTA = one 128 x BN output tile, 10 warps:
+//   warp 0 (1 thread)  bulk-copy producer: 3-stage ring, mbarrier expect_tx / complete_tx
+//   warp 1 (1 thread)  MMA issuer: 12 tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) per 32-wide K chunk,
+//                      tcgen05.commit frees the stage; owns the TMEM allocation (BN fp32 columns)
+//   warps 2-9          epilogue: tcgen05.ld (one accumulator row per thread) -> fused bias / GELU / GELU'
+//                      -> 128-byte-contiguous packed stores for the next GEMM (+ plain row stores)
+#include "sml_common.cuh"
+#include "umma_pack.cuh"
+
+namespace {
+
+constexpr int PKG_THREADS = 320;
+constexpr int PKG_EPI_THREADS = 256;
+constexpr int PKG_STAGES = 3;
+constexpr int PKG_MAX_PROBS = 4;
+
+struct PkParams { SmlPkProb p[PKG_MAX_PROBS]; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    // K-major, SWIZZLE_NONE, version 1; LBO / SBO in 16-byte units
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(PK_LBO >> 4) << 16) | ((uint64_t)(PK_SBO >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int BN> struct PkSmem {
+    static constexpr uint32_t A_BYTES = pk_block_bytes(128), B_BYTES = pk_block_bytes(BN);
+    static constexpr uint32_t STAGE = A_BYTES + B_BYTES;
+    static constexpr uint32_t TOTAL = PKG_STAGES * STAGE + 64;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(PKG_THREADS, 1)
+k_umma_packed(PkParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    using S = PkSmem<BN>;
+    const SmlPkProb p = P.p[blockIdx.z];
+    const int tile_m = blockIdx.y, tile_n = blockIdx.x;
+    if (tile_m >= p.m_tiles || tile_n * BN >= p.N) return;                    // nothing allocated yet
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + S::TOTAL - 64);
+    uint64_t *empty = full + PKG_STAGES;
+    uint64_t *done = empty + PKG_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::TOTAL - 8);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < PKG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const int KC = p.KC;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint8_t *a = p.A + (size_t)(p.a_tile0 + tile_m) * KC * S::A_BYTES;
+            const uint8_t *b = p.B + (size_t)tile_n * KC * S::B_BYTES;
+            for (int c = 0; c < KC; ++c) {
+                const int s = c % PKG_STAGES;
+                if (c >= PKG_STAGES) mbar_wait(&empty[s], ((c / PKG_STAGES) - 1) & 1);
+                uint8_t *st = smem + s * S::STAGE;
+                mbar_expect_tx(&full[s], S::STAGE);
+                bulk_g2s(st, a + (size_t)c * S::A_BYTES, S::A_BYTES, &full[s]);
+                bulk_g2s(st + S::A_BYTES, b + (size_t)c * S::B_BYTES, S::B_BYTES, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            for (int c = 0; c < KC; ++c) {
+                const int s = c % PKG_STAGES;
+                mbar_wait(&full[s], (c / PKG_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi = smem_u32(smem + s * S::STAGE), a_lo = a_hi + pk_half_bytes(128);
+                const uint32_t b_hi = a_hi + S::A_BYTES, b_lo = b_hi + pk_half_bytes(BN);
+#pragma unroll
+                for (int k = 0; k < PK_BK / 8; ++k) {
+                    const uint32_t ko = k * 2 * PK_LBO;
+                    const uint64_t ah = make_desc(a_hi + ko), al = make_desc(a_lo + ko), bh = make_desc(b_hi + ko), bl = make_desc(b_lo + ko);
+                    umma_tf32(tmem, al, bh, IDESC, (c | k) != 0);
+                    umma_tf32(tmem, ah, bl, IDESC, 1);
+                    umma_tf32(tmem, ah, bh, IDESC, 1);
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(done);
+        }
+    } else {
+        // ===== epilogue warps: straight from TMEM registers, one accumulator row per thread =====
+        mbar_wait(done, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int ew = warp - 2;                               // 0..7
+        const int quarter = warp & 3;                          // TMEM lane quarter this warp may access
+        const int r = quarter * 32 + lane;                     // accumulator row of this thread
+        const int chalf = ew >> 2;                             // the two warps of a quarter split the columns
+        const int n0 = tile_n * BN;
+        const int64_t m = p.row0 + (int64_t)tile_m * 128 + r;
+        const bool valid = tile_m * 128 + r < p.M;
+#pragma unroll
+        for (int c0 = chalf * (BN / 2); c0 < chalf * (BN / 2) + BN / 2; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + c0, v);
+            const int nb = n0 + c0;
+            if (EPI == SML_PK_FC1 || EPI == SML_PK_FC2) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + nb) + q);
+                    v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+                }
+            }
+            if (EPI == SML_PK_D2) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid) z = __ldg(reinterpret_cast<const float4 *>(p.aux + m * p.ldc + nb) + q);
+                    v[4 * q] *= sml_gelu_grad(z.x); v[4 * q + 1] *= sml_gelu_grad(z.y);
+                    v[4 * q + 2] *= sml_gelu_grad(z.z); v[4 * q + 3] *= sml_gelu_grad(z.w);
+                }
+            }
+            if (p.C && valid) {
+                // a thread writes 128 contiguous bytes of its row (the row pitch separates the lanes)
+                float4 *dst = reinterpret_cast<float4 *>(p.C + m * p.ldc + nb);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+            if ((EPI == SML_PK_FC1 || EPI == SML_PK_D2) && p.Cpk) {
+                // column nb.. of this GEMM = K index of the next one: one 32-wide K chunk, 8 quads; lanes r%8
+                // are 16 B apart => every store instruction writes whole 128 B core matrices
+                uint8_t *blk = p.Cpk + ((size_t)(p.c_tile0 + tile_m) * (p.N / PK_BK) + (nb >> 5)) * pk_block_bytes(128) +
+                               (uint32_t)(r >> 3) * PK_SBO + (uint32_t)(r & 7) * 16;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float h[4], l[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float x = (EPI == SML_PK_FC1) ? sml_gelu(v[4 * q + i]) : v[4 * q + i];
+                        pk_split(x, h[i], l[i]);
+                    }
+                    *reinterpret_cast<float4 *>(blk + q * PK_LBO) = make_float4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<float4 *>(blk + q * PK_LBO + pk_half_bytes(128)) = make_float4(l[0], l[1], l[2], l[3]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN) : "memory");
+}
+
+// ---- theta packer ---------------------------------------------------------------------------------
+// The four weight operands of one net, split and packed:  P1 = W1 as B[n=512][k=320] (128-row blocks),
+// P2 = W2 as B[64][512] (64-row), P3 = W2^T as B[512][64] (128-row), P4 = W1^T as B[320][512] (64-row).
+__global__ void __launch_bounds__(256) k_pack_theta(const float *__restrict__ theta, uint8_t *__restrict__ out, int n_nets) {
+    const int net = blockIdx.y >> 2, which = blockIdx.y & 3;
+    if (net >= n_nets) return;
+    const float *th = theta + (size_t)net * SML_NET_STRIDE;
+    uint8_t *dst = out + (size_t)net * SML_PK_THETA_BYTES;
+    const float *W; int R, K, ld, rows; bool tr;
+    if (which == 0) { W = th + SML_OFF_F1W; R = 512; K = 320; ld = 320; rows = 128; tr = false; dst += SML_PK_OFF_P1; }
+    else if (which == 1) { W = th + SML_OFF_F2W; R = 64; K = 512; ld = 512; rows = 64; tr = false; dst += SML_PK_OFF_P2; }
+    else if (which == 2) { W = th + SML_OFF_F2W; R = 512; K = 64; ld = 512; rows = 128; tr = true; dst += SML_PK_OFF_P3; }
+    else { W = th + SML_OFF_F1W; R = 320; K = 512; ld = 320; rows = 64; tr = true; dst += SML_PK_OFF_P4; }
+    const int KQ = K / 4, KC = K / 32;
+    const int total = R * KQ;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        int n, q;
+        float x[4];
+        if (!tr) {            // B[n][k] = W[n][k]: lanes along k (coalesced 16 B reads)
+            q = idx % KQ; n = idx / KQ;
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(W + (size_t)n * ld + 4 * q));
+            x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+        } else {              // B[n][k] = W[k][n]: lanes along n (coalesced 4 B reads, 128 B-contiguous packed stores)
+            n = idx % R; q = idx / R;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[i] = __ldg(W + (size_t)(4 * q + i) * ld + n);
+        }
+        float h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pk_split(x[i], h[i], l[i]);
+        const int tile = n / rows, r = n % rows, k = 4 * q;
+        uint8_t *blk = dst + ((size_t)tile * KC + (k >> 5)) * pk_block_bytes(rows) + pk_elem_off(r, k & 31);
+        *reinterpret_cast<float4 *>(blk) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4 *>(blk + pk_half_bytes(rows)) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+template <int BN, int EPI>
+int launch_pk(const PkParams &P, dim3 grid, cudaStream_t st) {
+    auto kern = k_umma_packed<BN, EPI>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SML_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PkSmem<BN>::TOTAL));
+        attr_set = true;
+    }
+    kern<<<grid, PKG_THREADS, PkSmem<BN>::TOTAL, st>>>(P);
+    SML_LAUNCH_OK();
+    return SML_OK;
+}
+
+}  // namespace
+
+int sml_launch_umma_packed(const SmlPkProb *probs, int n_probs, int epi, cudaStream_t st) {
+    SML_REQUIRE(n_probs >= 1 && n_probs <= PKG_MAX_PROBS, SML_E_BADARG, "packed gemm: bad problem count %d", n_probs);
+    PkParams P;
+    int max_mt = 0;
+    const int N = probs[0].N;
+    for (int i = 0; i < n_probs; ++i) {
+        P.p[i] = probs[i];
+        if (probs[i].m_tiles > max_mt) max_mt = probs[i].m_tiles;
+        SML_REQUIRE(probs[i].N == N && probs[i].KC >= 1, SML_E_BADARG, "packed gemm: grouped problems must share N and have KC >= 1");
+    }
+    if (max_mt == 0) return SML_OK;
+    switch (epi) {
+        case SML_PK_FC1: SML_REQUIRE(N % 128 == 0, SML_E_BADARG, "packed gemm: fc1 N"); return launch_pk<128, SML_PK_FC1>(P, dim3(N / 128, max_mt, n_probs), st);
+        case SML_PK_FC2: SML_REQUIRE(N % 64 == 0, SML_E_BADARG, "packed gemm: fc2 N"); return launch_pk<64, SML_PK_FC2>(P, dim3(N / 64, max_mt, n_probs), st);
+        case SML_PK_D2: SML_REQUIRE(N % 128 == 0, SML_E_BADARG, "packed gemm: d2 N"); return launch_pk<128, SML_PK_D2>(P, dim3(N / 128, max_mt, n_probs), st);
+        case SML_PK_D1: SML_REQUIRE(N % 64 == 0, SML_E_BADARG, "packed gemm: d1 N"); return launch_pk<64, SML_PK_D1>(P, dim3(N / 64, max_mt, n_probs), st);
+    }
+    sml_set_error("packed gemm: bad epilogue %d", epi);
+    return SML_E_BADARG;
+}
+
+int sml_launch_pack_theta(const float *theta, uint8_t *out, int n_nets, cudaStream_t st) {
+    dim3 grid(40, 4 * n_nets);
+    k_pack_theta<<<grid, 256, 0, st>>>(theta, out, n_nets);
+    SML_LAUNCH_OK();
+    return SML_OK;
+}

@@ -130,7 +130,8 @@ class _FlatTransfer(nn.Module):
         ar = torch.arange(2 * B, dtype=torch.int64, device=dev)
         last_item = torch.cat([i_last, j_last]); hat_item = torch.cat([i_hat, j_hat])
         loss_out = torch.zeros(2, dtype=torch.float32, device=dev)
-        d_rows = torch.empty(3 * B, 64, dtype=torch.float32, device=dev) if need_grad else None
+        total, rp, rn = ops.step_rows(B)
+        d_rows = torch.zeros(total, 64, dtype=torch.float32, device=dev) if need_grad else None
         args = ops.make_step_args(user=ar[:B], item=ar[:B], neg=ar[B:], last_user=u_last, last_item=last_item,
                                   hat_user=u_hat, hat_item=hat_item, theta=self.theta, variant=self.variant, loss=loss_kind,
                                   g_theta=self.theta_grad if need_grad else None, loss_out=loss_out,
@@ -138,6 +139,8 @@ class _FlatTransfer(nn.Module):
         if need_grad:
             self.theta_grad.zero_()
         ops.run_mf_grads(args, d_rows=d_rows)
+        if d_rows is not None:
+            d_rows = torch.cat([d_rows[:B], d_rows[rp:rp + B], d_rows[rn:rn + B]])
         return loss_out[0], d_rows
 
 

@@ -111,6 +111,13 @@ def step_workspace(batch, device, tag="step"):
     return _workspace(lib().sml_step_workspace_bytes(batch), device, tag)
 
 
+def step_rows(batch):
+    """-> (total padded rows, first positive-item row, first negative-item row) of the per-step matrices."""
+    rp, rn = C.c_int64(), C.c_int64()
+    total = lib().sml_step_rows(batch, C.byref(rp), C.byref(rn))
+    return int(total), int(rp.value), int(rn.value)
+
+
 def make_step_args(*, user, item, neg, last_user, last_item, hat_user, hat_item, theta, variant=VARIANT_COM, loss=LOSS_BCE,
                    g_user=None, g_item=None, m_user=None, v_user=None, m_item=None, v_item=None, adam_state=None,
                    lr=0.0, l2=0.0, g_theta=None, m_theta=None, v_theta=None, loss_out=None, workspace=None, batch=None):
