@@ -106,7 +106,7 @@ struct SmlGemmProb {
 int sml_launch_sgemm(const SmlGemmProb *probs, int n_probs, int a_mode, int b_mode, int epi, cudaStream_t st);
 // tcgen05 3xTF32 GEMM, same contract (+ transposed store: C[n][m]); bn = 64 | 128
 int sml_launch_umma_gemm(const SmlGemmProb *probs, int n_probs, int a_mode, int b_mode, int epi, int transpose_out, int bn,
-                         cudaStream_t st);
+                         cudaStream_t st, int ksplit = 1);
 // 1 = tensor-core GEMMs (default), 0 = SIMT fp32 GEMMs (SML_GEMM=simt in the environment, for A/B comparisons)
 int sml_use_tensor_cores();
 

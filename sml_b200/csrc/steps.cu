@@ -182,12 +182,15 @@ int fc_wgrads(const sml_step_args *a, const StepWs &w, float *g_theta, cudaStrea
     const int64_t B = r.B, Bp = r.Bp;
     float *gu = g_theta, *gi = g_theta + SML_NET_STRIDE;
     int rc;
+    // the reduction runs over the batch rows (K = B or 2B): slice it so the few output tiles (4 for dW2,
+    // 20 for dW1 per net) spread over the SMs; slices combine with fp32 atomics
+    const int ksplit = B >= 2048 ? 16 : (B >= 128 ? 8 : 1);
     if (sml_use_tensor_cores()) {
         // tensor-core tiles are 128 rows tall: compute dW2^T [512, 64] = g(Z1)^T dY and store it transposed
         SmlGemmProb w2t[2] = {
             {w.Z1, w.dY, nullptr, nullptr, gu + SML_OFF_F2W, 512, 64, (int)B, 512, 64, 512},
             {w.Z1 + Bp * 512, w.dY + Bp * 64, nullptr, nullptr, gi + SML_OFF_F2W, 512, 64, (int)(2 * B), 512, 64, 512}};
-        rc = sml_launch_umma_gemm(w2t, 2, SML_A_KM_GELU, SML_B_KN, SML_EPI_ACCUM, 1, 64, st);
+        rc = sml_launch_umma_gemm(w2t, 2, SML_A_KM_GELU, SML_B_KN, SML_EPI_ACCUM, 1, 64, st, ksplit);
     } else {
         SmlGemmProb w2[2] = {
             {w.dY, w.Z1, nullptr, nullptr, gu + SML_OFF_F2W, 64, 512, (int)B, 64, 512, 512},
@@ -198,7 +201,7 @@ int fc_wgrads(const sml_step_args *a, const StepWs &w, float *g_theta, cudaStrea
     SmlGemmProb w1[2] = {
         {w.dZ1, w.A, nullptr, nullptr, gu + SML_OFF_F1W, 512, 320, (int)B, 512, 320, 320},
         {w.dZ1 + Bp * 512, w.A + Bp * 320, nullptr, nullptr, gi + SML_OFF_F1W, 512, 320, (int)(2 * B), 512, 320, 320}};
-    if (sml_use_tensor_cores()) rc = sml_launch_umma_gemm(w1, 2, SML_A_KM, SML_B_KN, SML_EPI_ACCUM, 0, 64, st);
+    if (sml_use_tensor_cores()) rc = sml_launch_umma_gemm(w1, 2, SML_A_KM, SML_B_KN, SML_EPI_ACCUM, 0, 64, st, ksplit > 2 ? ksplit / 2 : 1);
     else rc = sml_launch_sgemm(w1, 2, SML_A_KM, SML_B_KN, SML_EPI_ACCUM, st);
     if (rc) return rc;
     SmlColsumProb cs[4] = {{w.dY, gu + SML_OFF_F2B, (int)B, 64, 64},

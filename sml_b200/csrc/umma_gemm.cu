@@ -37,7 +37,7 @@ constexpr uint32_t UM_LBO = 144;           // bytes between K-adjacent core matr
 constexpr uint32_t UM_SBO = 8 * UM_LBO;    // bytes between 8-row groups (1152)
 constexpr int UM_MAX_PROBS = 4;
 
-struct UmmaParams { SmlGemmProb p[UM_MAX_PROBS]; int transpose_out; };
+struct UmmaParams { SmlGemmProb p[UM_MAX_PROBS]; int transpose_out; int ksplit; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -186,7 +186,19 @@ __global__ void __launch_bounds__(UM_CTA_THREADS, 1)
 k_umma_gemm(UmmaParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     using S = Smem<BN>;
-    const SmlGemmProb p = P.p[blockIdx.z];
+    // split-K: blockIdx.z = problem * ksplit + slice; a slice owns a 32-aligned K range and, when there is
+    // more than one slice, adds its partial product into C with atomics (EPI_ACCUM only)
+    SmlGemmProb p = P.p[blockIdx.z / P.ksplit];
+    {
+        const int per = ((p.K + UM_BK - 1) / UM_BK + P.ksplit - 1) / P.ksplit * UM_BK;
+        const int kbeg = (int)(blockIdx.z % P.ksplit) * per;
+        if (kbeg >= p.K) return;
+        const int kend = kbeg + per < p.K ? kbeg + per : p.K;
+        p.A += A_KCONTIG ? (size_t)kbeg : (size_t)kbeg * p.lda;
+        p.B += B_KCONTIG ? (size_t)kbeg : (size_t)kbeg * p.ldb;
+        p.K = kend - kbeg;
+    }
+    const bool atomic_acc = P.ksplit > 1;
     const int m0 = blockIdx.y * UM_BM, n0 = blockIdx.x * BN;
     if (m0 >= p.M || n0 >= p.N) return;                       // whole CTA exits: nothing allocated yet
     // mbarriers: full[s] (256 producer arrivals), empty[s] (1 tcgen05.commit), done (1 commit)
@@ -302,6 +314,7 @@ k_umma_gemm(UmmaParams P) {
                 if (EPI == SML_EPI_BIAS) v += p.bias[n];
                 if (EPI == SML_EPI_MUL_GELU_GRAD) v *= sml_gelu_grad(p.aux[(size_t)m * p.ldc + n]);
                 float *dst = p.C + (size_t)m * p.ldc + n;
+                if (EPI == SML_EPI_ACCUM && atomic_acc) { atomicAdd(dst, v); continue; }
                 if (EPI == SML_EPI_ACCUM) v += *dst;
                 *dst = v;
             }
@@ -314,6 +327,7 @@ k_umma_gemm(UmmaParams P) {
             if (m < p.M && n < p.N) {
                 float v = epi[r * (BN + 1) + cc];
                 float *dst = p.C + (size_t)n * p.ldc + m;
+                if (EPI == SML_EPI_ACCUM && atomic_acc) { atomicAdd(dst, v); continue; }
                 if (EPI == SML_EPI_ACCUM) v += *dst;
                 *dst = v;
             }
@@ -362,13 +376,15 @@ int launch_bn(const UmmaParams &P, dim3 grid, int a_mode, int b_mode, int epi, c
 
 // Same contract as sml_launch_sgemm plus transpose_out (C stored [n][m]); bn = 64 or 128.
 int sml_launch_umma_gemm(const SmlGemmProb *probs, int n_probs, int a_mode, int b_mode, int epi, int transpose_out, int bn,
-                         cudaStream_t st) {
+                         cudaStream_t st, int ksplit) {
+    SML_REQUIRE(ksplit >= 1 && (ksplit == 1 || epi == SML_EPI_ACCUM), SML_E_BADARG, "umma gemm: split-K needs the accumulate epilogue");
     SML_REQUIRE(n_probs >= 1 && n_probs <= UM_MAX_PROBS, SML_E_BADARG, "umma gemm: bad problem count %d", n_probs);
     SML_REQUIRE(bn == 64 || bn == 128, SML_E_BADARG, "umma gemm: bn must be 64 or 128");
     SML_REQUIRE(!(transpose_out && (epi == SML_EPI_BIAS || epi == SML_EPI_MUL_GELU_GRAD)), SML_E_BADARG,
                 "umma gemm: transposed store supports only the plain / accumulate epilogues");
     UmmaParams P;
     P.transpose_out = transpose_out;
+    P.ksplit = ksplit;
     int maxM = 0, maxN = 0;
     for (int i = 0; i < n_probs; ++i) {
         P.p[i] = probs[i];
@@ -378,6 +394,6 @@ int sml_launch_umma_gemm(const SmlGemmProb *probs, int n_probs, int a_mode, int 
         SML_REQUIRE(probs[i].K >= 1, SML_E_BADARG, "umma gemm: K must be positive");
     }
     if (maxM == 0 || maxN == 0) return SML_OK;
-    dim3 grid((maxN + bn - 1) / bn, (maxM + UM_BM - 1) / UM_BM, n_probs);
+    dim3 grid((maxN + bn - 1) / bn, (maxM + UM_BM - 1) / UM_BM, n_probs * ksplit);
     return bn == 64 ? launch_bn<64>(P, grid, a_mode, b_mode, epi, st) : launch_bn<128>(P, grid, a_mode, b_mode, epi, st);
 }
