@@ -221,42 +221,45 @@ def run_ours(a):
     sys.stdout = quiet                                   # the drop-in prints like the reference; keep the JSON line clean
     try:
         # ---------------- e2e arm: host arrays, H2D/D2H inside the timed region ----------------
-        pin = lambda x: torch.from_numpy(x).pin_memory().numpy()          # inputs live in pinned host memory
-        e2e_periods = [(pin(tr), pin(te)) for tr, te in periods[:W + K + 1]]
-        ds = MemoryStream(e2e_periods, U, I)
-        meta = meta_train(args, ds, U, I, 64, device=dev)
-        h2d = [0]
-        orig_to_device, orig_upload = meta._to_device, meta._upload
-
-        def to_device(arr):
-            if id(arr) not in meta._dev_cache:
-                h2d[0] += arr.size * 8
-            return orig_to_device(arr)
-
-        def upload(arrs):
-            h2d[0] += sum(int(np.asarray(x).size) * 8 for x in arrs)
-            return orig_upload(arrs)
-        meta._to_device, meta._upload = to_device, upload
-        stage = 0
-        for _ in range(W):
-            meta._dev_cache.clear()
-            meta.train_one_stage3(args, stage); stage += 1
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        h2d[0] = 0
-        t0 = time.perf_counter()
-        for _ in range(K):
-            meta._dev_cache.clear()                      # nothing of this period is resident when its step starts
-            meta.train_one_stage3(args, stage); stage += 1
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
+        e2e_s, e2e_h2d, e2e_d2h = float("nan"), 0, 0
         mf_steps, tr_steps, n_updata, n_evals = period_counts(shape["rows"])
-        e2e_h2d = h2d[0] / K
-        e2e_d2h = (n_evals * 8 + (HYPER["multi_num"] * (HYPER["MF_epochs"] + HYPER["TR_epochs"])) * 4)
-        if world > 1:
-            t = torch.tensor([e2e_s], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t)
-        del meta, e2e_periods
+        if not a.skip_e2e:
+            pin = lambda x: torch.from_numpy(x).pin_memory().numpy()          # inputs live in pinned host memory
+            e2e_periods = [(pin(tr), pin(te)) for tr, te in periods[:W + K + 1]]
+            ds = MemoryStream(e2e_periods, U, I)
+            meta = meta_train(args, ds, U, I, 64, device=dev)
+            h2d = [0]
+            orig_to_device, orig_upload = meta._to_device, meta._upload
+
+            def to_device(arr):
+                if id(arr) not in meta._dev_cache:
+                    h2d[0] += arr.size * 8
+                return orig_to_device(arr)
+
+            def upload(arrs):
+                h2d[0] += sum(int(np.asarray(x).size) * 8 for x in arrs)
+                return orig_upload(arrs)
+            meta._to_device, meta._upload = to_device, upload
+            stage = 0
+            for _ in range(W):
+                meta._dev_cache.clear()
+                meta.train_one_stage3(args, stage); stage += 1
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            h2d[0] = 0
+            t0 = time.perf_counter()
+            for _ in range(K):
+                meta._dev_cache.clear()                      # nothing of this period is resident when its step starts
+                meta.train_one_stage3(args, stage); stage += 1
+            torch.cuda.synchronize()
+            e2e_s = time.perf_counter() - t0
+            mf_steps, tr_steps, n_updata, n_evals = period_counts(shape["rows"])
+            e2e_h2d = h2d[0] / K
+            e2e_d2h = (n_evals * 8 + (HYPER["multi_num"] * (HYPER["MF_epochs"] + HYPER["TR_epochs"])) * 4)
+            if world > 1:
+                t = torch.tensor([e2e_s], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t)
+            del meta, e2e_periods
 
         # ---------------- resident arm: everything in HBM before the clock starts ----------------
         res_periods = periods[W + K:]
@@ -356,7 +359,8 @@ def run_ours(a):
                    "l2_flush": "inputs larger than L2: each step streams 2 x 600 MB period files and 47 MB x 7 table copies",
                    "parallelism": "1 replica stream per GPU" if world > 1 else "single GPU"},
         "samples_per_s": world * K * (HYPER["multi_num"] * shape["rows"] * (HYPER["MF_epochs"] + HYPER["TR_epochs"])) / dev_s,
-        "e2e": {"value": world * K / e2e_s, "unit": "periods/s", "h2d_bytes_per_step": int(e2e_h2d), "d2h_bytes_per_step": int(e2e_d2h)},
+        "e2e": {"value": (world * K / e2e_s) if e2e_s == e2e_s else None, "unit": "periods/s", "h2d_bytes_per_step": int(e2e_h2d),
+                "d2h_bytes_per_step": int(e2e_d2h)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "phases_ms_per_period": {k: v[1] / K for k, v in phases.items()},
@@ -383,6 +387,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=0, help="rows per period (default: the Yelp shape, 75000)")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--skip-e2e", dest="skip_e2e", action="store_true", help="profiling runs only: skip the host-buffer arm")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference_arm(a)
