@@ -154,9 +154,12 @@ typedef struct {
     /* outputs */
     float *loss_out; /* [2]: loss_out[0] = this step's loss (as the reference's loss_batch),      */
                      /*      loss_out[1] += loss (the reference's loss_all accumulation, :501,722) */
-    /* scratch */
+    /* scratch (zero-initialised by the caller before its first use) */
     void *workspace;
     size_t workspace_bytes;
+    /* floats between consecutive rows of last_* / hat_* (0 = 64).  sml_run_mf_grads only: lets the four
+     * "tables" be views into exchanged [last | hat] row pairs (pitch 128) without a de-interleave copy. */
+    int64_t table_pitch;
 } sml_step_args;
 
 size_t sml_step_workspace_bytes(int64_t batch);
@@ -182,6 +185,16 @@ int sml_tr_epoch(const sml_step_args *args, int64_t n_total, void *stream);
  * term; row layout of sml_step_rows) if non-null and accumulates theta gradients into args->g_theta if
  * non-null. */
 int sml_run_mf_grads(const sml_step_args *args, float *d_rows, float *scores /* [2B] s+, s- or null */, void *stream);
+
+/* ---- row exchange for row-sharded tables (north_star item 4) ---------------------------------
+ * Tables are sharded by id (owner = id % world, local row = id / world).  Owner side of the exchange:
+ *   sml_gather_pairs : out[n] = [last[loc[n]] | hat[loc[n]]]   (2*d floats per id; answers an id request)
+ *   sml_scatter_grads: g[loc[n]] += scale * d_rows[n] + l2 * hat[loc[n]]   (row gradients that came back;
+ *                      the l2 term of model/transfer.py:486 is added per occurrence by the owner)
+ * The NCCL all-to-all between them is issued by the host side (sml_b200/shard.py). */
+int sml_gather_pairs(const float *last, const float *hat, const int64_t *loc, int64_t n, int d, float *out, void *stream);
+int sml_scatter_grads(float *g, const float *hat, const int64_t *loc, const float *d_rows, int64_t n, int d, double scale,
+                      double l2, void *stream);
 
 /* ---- host helper (all pointers are HOST pointers) ------------------------------------------
  * The sequential walk of offlineDataset_withsample's rejection sampler (data/dataset.py:62-71): sample s

@@ -32,7 +32,7 @@ class StepArgs(C.Structure):
         ("g_user", _vp), ("g_item", _vp), ("m_user", _vp), ("v_user", _vp), ("m_item", _vp), ("v_item", _vp),
         ("adam_state", _vp), ("lr", _dbl), ("l2", _dbl),
         ("g_theta", _vp), ("m_theta", _vp), ("v_theta", _vp),
-        ("loss_out", _vp), ("workspace", _vp), ("workspace_bytes", _sz),
+        ("loss_out", _vp), ("workspace", _vp), ("workspace_bytes", _sz), ("table_pitch", _i64),
     ]
 
 
@@ -56,6 +56,8 @@ _PROTOS = {
     "sml_mf_epoch": (_i32, [C.POINTER(StepArgs), _i64, _vp]),
     "sml_tr_epoch": (_i32, [C.POINTER(StepArgs), _i64, _vp]),
     "sml_run_mf_grads": (_i32, [C.POINTER(StepArgs), _vp, _vp, _vp]),
+    "sml_gather_pairs": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "sml_scatter_grads": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _dbl, _dbl, _vp]),
     "sml_host_rejection_walk": (_i64, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
     "sml_debug_gemm": (_i32, [_vp, _vp, _vp, _vp, _vp] + [_i32] * 12 + [_vp]),
     "sml_plain_mf_grads": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -77,8 +77,8 @@ k_conv_fwd(ConvParams P, float *__restrict__ A, uint8_t *__restrict__ Apk, float
     const int64_t nwarps = (int64_t)gridDim.x * CONV_WARPS;
     for (int64_t r = warp0; r < g.n; r += nwarps) {
         const int64_t id = g.ids ? __ldg(g.ids + r) : r;
-        const float *xt = g.x_t + id * SML_D;
-        const float *xh = g.x_hat + id * SML_D;
+        const float *xt = g.x_t + id * g.pitch;
+        const float *xh = g.x_hat + id * g.pitch;
         float x0[2] = {__ldg(xt + lane), __ldg(xt + lane + 32)};
         float x1[2] = {__ldg(xh + lane), __ldg(xh + lane + 32)};
         float x2[2] = {0.f, 0.f};
@@ -146,8 +146,8 @@ k_conv_bwd(ConvBwdParams P, const float *__restrict__ dA, float l2, float *__res
     }
     for (int64_t r = warp0; r < g.n; r += nwarps) {
         const int64_t id = g.ids ? __ldg(g.ids + r) : r;
-        const float *xt = g.x_t + id * SML_D;
-        const float *xh = g.x_hat + id * SML_D;
+        const float *xt = g.x_t + id * g.pitch;
+        const float *xh = g.x_hat + id * g.pitch;
         float x0[2] = {__ldg(xt + lane), __ldg(xt + lane + 32)};
         float x1[2] = {__ldg(xh + lane), __ldg(xh + lane + 32)};
         float x2[2] = {0.f, 0.f};

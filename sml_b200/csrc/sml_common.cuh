@@ -77,6 +77,7 @@ struct SmlRowGroup {
     const float *theta;  // this group's net
     int64_t n;           // rows in the group
     int64_t row0;        // first row of the group in the packed [N, .] workspace matrices
+    int64_t pitch;       // floats between consecutive source rows (64 for tables, 128 for exchanged [last|hat] pairs)
 };
 
 // conv prologue: fc1 input for every row of the groups, as plain A[N,320] (or null) and/or as a packed

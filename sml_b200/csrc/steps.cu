@@ -79,15 +79,17 @@ int check_args(const sml_step_args *a, const char *who) {
     SML_REQUIRE(a->workspace && a->workspace_bytes >= step_ws_bytes(a->batch), SML_E_WORKSPACE,
                 "%s: workspace too small (%zu < %zu bytes)", who, a->workspace_bytes, step_ws_bytes(a->batch));
     SML_REQUIRE(a->loss_out, SML_E_BADARG, "%s: null loss_out", who);
+    SML_REQUIRE(a->table_pitch == 0 || (a->table_pitch >= SML_D && a->table_pitch % 4 == 0), SML_E_BADARG, "%s: bad table_pitch", who);
     return SML_OK;
 }
 
 void make_groups(const sml_step_args *a, SmlRowGroup g[3]) {
     const Rows r = rows_of(a->batch);
     const float *tu = a->theta, *ti = a->theta + SML_NET_STRIDE;
-    g[0] = SmlRowGroup{a->last_user, a->hat_user, a->user, tu, r.B, 0};
-    g[1] = SmlRowGroup{a->last_item, a->hat_item, a->item, ti, r.B, r.Bp};
-    g[2] = SmlRowGroup{a->last_item, a->hat_item, a->neg, ti, r.B, r.Bp + r.B};
+    const int64_t pitch = a->table_pitch > 0 ? a->table_pitch : SML_D;
+    g[0] = SmlRowGroup{a->last_user, a->hat_user, a->user, tu, r.B, 0, pitch};
+    g[1] = SmlRowGroup{a->last_item, a->hat_item, a->item, ti, r.B, r.Bp, pitch};
+    g[2] = SmlRowGroup{a->last_item, a->hat_item, a->neg, ti, r.B, r.Bp + r.B, pitch};
 }
 
 // two-net problem pair for the packed GEMMs
@@ -236,6 +238,7 @@ int check_mf(const sml_step_args *a) {
     if (rc) return rc;
     rc = check_args(a, "sml_mf_step");
     if (rc) return rc;
+    SML_REQUIRE(a->table_pitch == 0 || a->table_pitch == SML_D, SML_E_BADARG, "sml_mf_step: tables must be dense [rows, 64]");
     SML_REQUIRE(a->g_user && a->g_item && a->m_user && a->v_user && a->m_item && a->v_item && a->adam_state, SML_E_BADARG,
                 "sml_mf_step: null gradient / Adam-state pointer");
     return SML_OK;
@@ -290,8 +293,8 @@ int sml_transfer_fwd(const float *x_t, const float *x_hat, const int64_t *ids, i
     for (int64_t r0 = 0; r0 < n_rows; r0 += ch) {
         const int64_t n = (n_rows - r0) < ch ? (n_rows - r0) : ch;
         SmlRowGroup g;
-        if (ids) g = SmlRowGroup{x_t, x_hat, ids + r0, theta_net, n, 0};
-        else g = SmlRowGroup{x_t + r0 * SML_D, x_hat + r0 * SML_D, nullptr, theta_net, n, 0};
+        if (ids) g = SmlRowGroup{x_t, x_hat, ids + r0, theta_net, n, 0, SML_D};
+        else g = SmlRowGroup{x_t + r0 * SML_D, x_hat + r0 * SML_D, nullptr, theta_net, n, 0, SML_D};
         rc = sml_launch_conv_fwd(&g, 1, variant, tc ? nullptr : A, tc ? Apk : nullptr, nullptr, st);
         if (rc) return rc;
         if (tc) {

@@ -120,13 +120,17 @@ def step_rows(batch):
 
 def make_step_args(*, user, item, neg, last_user, last_item, hat_user, hat_item, theta, variant=VARIANT_COM, loss=LOSS_BCE,
                    g_user=None, g_item=None, m_user=None, v_user=None, m_item=None, v_item=None, adam_state=None,
-                   lr=0.0, l2=0.0, g_theta=None, m_theta=None, v_theta=None, loss_out=None, workspace=None, batch=None):
+                   lr=0.0, l2=0.0, g_theta=None, m_theta=None, v_theta=None, loss_out=None, workspace=None, batch=None,
+                   table_pitch=0, n_users=None, n_items=None):
     a = StepArgs()
     B = user.numel() if batch is None else int(batch)
     a.user, a.item, a.neg, a.batch = ptr(_i64(user, "user")), ptr(_i64(item, "item")), ptr(_i64(neg, "neg")), B
-    a.last_user, a.last_item = ptr(_f32(last_user, "last_user")), ptr(_f32(last_item, "last_item"))
-    a.hat_user, a.hat_item = ptr(_f32(hat_user, "hat_user")), ptr(_f32(hat_item, "hat_item"))
-    a.n_users, a.n_items = hat_user.shape[0], hat_item.shape[0]
+    _p = (lambda t: ptr(t)) if table_pitch in (0, D) else (lambda t: t.data_ptr())     # pitched views are not contiguous
+    a.last_user, a.last_item = _p(_f32(last_user, "last_user")), _p(_f32(last_item, "last_item"))
+    a.hat_user, a.hat_item = _p(_f32(hat_user, "hat_user")), _p(_f32(hat_item, "hat_item"))
+    a.n_users = hat_user.shape[0] if n_users is None else n_users
+    a.n_items = hat_item.shape[0] if n_items is None else n_items
+    a.table_pitch = table_pitch
     a.theta, a.variant, a.loss = ptr(_f32(theta, "theta")), variant, loss
     a.g_user, a.g_item = ptr(g_user), ptr(g_item)
     a.m_user, a.v_user, a.m_item, a.v_item = ptr(m_user), ptr(v_user), ptr(m_item), ptr(v_item)
@@ -160,6 +164,20 @@ def tr_epoch(args, n_total):
 
 def run_mf_grads(args, d_rows=None, scores=None):
     check(lib().sml_run_mf_grads(C.byref(args), ptr(d_rows), ptr(scores), stream()), "run_mf_grads")
+
+
+def gather_pairs(last, hat, loc):
+    """Owner side of the row exchange: [n, 128] = [last[loc] | hat[loc]]."""
+    n = loc.numel()
+    out = torch.empty(n, 2 * D, dtype=torch.float32, device=last.device)
+    check(lib().sml_gather_pairs(ptr(last), ptr(hat), ptr(_i64(loc, "loc")), n, D, ptr(out), stream()), "gather_pairs")
+    return out
+
+
+def scatter_grads(g, hat, loc, d_rows, scale=1.0, l2=0.0):
+    """Owner side: g[loc] += scale * d_rows + l2 * hat[loc]."""
+    check(lib().sml_scatter_grads(ptr(g), ptr(hat), ptr(_i64(loc, "loc")), ptr(d_rows), loc.numel(), D, scale, l2, stream()),
+          "scatter_grads")
 
 
 def plain_mf_grads(user_tab, item_tab, user, item, neg, g_user, g_item, loss_out, loss=LOSS_BCE, l2_u=0.0, l2_i=0.0,

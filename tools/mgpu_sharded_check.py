@@ -1,0 +1,90 @@
+"""torchrun --nproc-per-node N tools/mgpu_sharded_check.py : the N-rank sharded MF / transfer steps (NCCL
+all-to-all row exchange, theta all-reduce) against the same global batch run on one GPU with the fused steps.
+Also times sharded steps on scaled synthetic tables (rows per GPU fixed: weak scaling of the table size)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import sml_oracle as O  # noqa: E402  (checker only)
+from sml_b200 import ops  # noqa: E402
+from sml_b200.model.conv_transfer import ConvTransfer_com  # noqa: E402
+from sml_b200.shard import ShardedSML, shard_rows  # noqa: E402
+
+
+def module(tu, ti, dev):
+    import contextlib, io
+    with torch.random.fork_rng(devices=[]), contextlib.redirect_stdout(io.StringIO()):
+        m = ConvTransfer_com(64, 64).to(dev)
+    sd = {("user_transfer." + k): torch.from_numpy(v) for k, v in tu.items()}
+    sd.update({("item_transfer." + k): torch.from_numpy(v) for k, v in ti.items()})
+    m.load_state_dict(sd)
+    return m
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    rng = np.random.default_rng(0)
+    U, I, B = 4000, 6000, 256 * world
+    ut = rng.standard_normal((U, 64)).astype(np.float32); it = rng.standard_normal((I, 64)).astype(np.float32)
+    tu, ti = O.init_theta(np.random.default_rng(1)), O.init_theta(np.random.default_rng(2))
+    ids = [rng.integers(0, n, B).astype(np.int64) for n in (U, I, I)]
+    res = {}
+    # single-GPU fused reference on rank 0's device (every rank computes it: cheap)
+    m1 = module(tu, ti, dev)
+    u1, i1 = T(ut), T(it)
+    z = {k: torch.zeros_like(u1 if "user" in k else i1) for k in ("m_user", "v_user", "m_item", "v_item", "g_user", "g_item")}
+    loss = torch.zeros(2, device=dev)
+    a = ops.make_step_args(user=T(ids[0]), item=T(ids[1]), neg=T(ids[2]), last_user=T(ut), last_item=T(it), hat_user=u1, hat_item=i1,
+                           theta=m1.theta, adam_state=ops.new_adam_state(dev), lr=0.01, l2=1e-6, loss_out=loss, **z)
+    ops.mf_step(a)
+    m2 = module(tu, ti, dev)
+    s = ShardedSML(shard_rows(T(ut), world, rank), shard_rows(T(it), world, rank), m2, world=world, rank=rank, mf_lr=0.01, l2=1e-6)
+    sl = slice(rank * (B // world), (rank + 1) * (B // world))
+    s.mf_step(T(ids[0][sl]), T(ids[1][sl]), T(ids[2][sl]))
+    res["mf_user_maxdiff"] = float((s.user - u1[rank::world]).abs().max())
+    res["mf_item_maxdiff"] = float((s.item - i1[rank::world]).abs().max())
+    s.save_hat()
+    mm, vv = torch.zeros_like(m1.theta), torch.zeros_like(m1.theta)
+    a = ops.make_step_args(user=T(ids[0]), item=T(ids[1]), neg=T(ids[2]), last_user=T(ut), last_item=T(it), hat_user=u1, hat_item=i1,
+                           theta=m1.theta, adam_state=ops.new_adam_state(dev), lr=0.001, l2=1e-4, g_theta=m1.theta_grad, m_theta=mm,
+                           v_theta=vv, loss_out=loss)
+    ops.tr_step(a)
+    s.tr_step(T(ids[0][sl]), T(ids[1][sl]), T(ids[2][sl]))
+    res["tr_theta_maxdiff"] = float((m2.theta - m1.theta).abs().max())
+    ok = res["mf_user_maxdiff"] < 1e-5 and res["mf_item_maxdiff"] < 1e-5 and res["tr_theta_maxdiff"] < 1e-5
+    # ---- throughput on scaled tables: rows per GPU fixed ----
+    Ul, Il, Bl = int(os.environ.get("SML_ROWS_PER_GPU", 4_000_000)), int(os.environ.get("SML_ITEMS_PER_GPU", 1_000_000)), 8192
+    g = torch.Generator(device=dev).manual_seed(rank)
+    big = ShardedSML(torch.randn(Ul, 64, device=dev, generator=g), torch.randn(Il, 64, device=dev, generator=g), m2, world=world, rank=rank)
+    gu = lambda n, hi: torch.randint(0, hi, (n,), device=dev, generator=g)
+    for kind, fn in (("mf", big.mf_step), ("tr", big.tr_step)):
+        for _ in range(3):
+            fn(gu(Bl, Ul * world), gu(Bl, Il * world), gu(Bl, Il * world))
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            fn(gu(Bl, Ul * world), gu(Bl, Il * world), gu(Bl, Il * world))
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 10], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res["%s_step_ms" % kind] = float(t)
+        res["%s_triples_per_s" % kind] = Bl * world / float(t) * 1e3
+    res.update(world=world, ok=bool(ok), rows_per_gpu=Ul + Il, batch_per_gpu=Bl)
+    if rank == 0:
+        print(json.dumps(res))
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
