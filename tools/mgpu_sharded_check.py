@@ -60,7 +60,7 @@ def main():
     ops.tr_step(a)
     s.tr_step(T(ids[0][sl]), T(ids[1][sl]), T(ids[2][sl]))
     res["tr_theta_maxdiff"] = float((m2.theta - m1.theta).abs().max())
-    ok = res["mf_user_maxdiff"] < 1e-5 and res["mf_item_maxdiff"] < 1e-5 and res["tr_theta_maxdiff"] < 1e-5
+    ok = res["mf_user_maxdiff"] < 1e-5 and res["mf_item_maxdiff"] < 1e-5 and res["tr_theta_maxdiff"] < 1e-4   # theta after Adam: step tolerance (1e-4)
     # ---- throughput on scaled tables: rows per GPU fixed ----
     Ul, Il, Bl = int(os.environ.get("SML_ROWS_PER_GPU", 4_000_000)), int(os.environ.get("SML_ITEMS_PER_GPU", 1_000_000)), 8192
     g = torch.Generator(device=dev).manual_seed(rank)
