@@ -186,6 +186,20 @@ int sml_tr_epoch(const sml_step_args *args, int64_t n_total, void *stream);
  * non-null. */
 int sml_run_mf_grads(const sml_step_args *args, float *d_rows, float *scores /* [2B] s+, s- or null */, void *stream);
 
+/* ---- full-catalog evaluation (north_star item 3 / config 5) ----------------------------------
+ * rank of every evaluated (user, positive item) pair among ALL items: a tcgen05 3xTF32 score GEMM
+ * [users x 64] x [64 x items] with a fused compare-and-count epilogue.
+ *   sml_pack_rows   : rows of a [*, 64] table (gathered by ids, or rows 0..n-1 when ids is null) -> packed
+ *                     tensor-core operand (sml_packed_rows_bytes(n) bytes)
+ *   sml_fullcat_rank: gt[u] += #{i : s_ui > s_pos[u]}, eq[u] += #{i : s_ui == s_pos[u]} over the n_items items of
+ *                     items_packed whose global ids start at item_id0; the item with id pos_id[u] is skipped.
+ *                     gt / eq must be zeroed by the caller; item shards on several GPUs add up (all-reduce).
+ * s_pos[u] = <user_u, item_pos_u> comes from sml_pair_scores (fp32 FFMA). */
+size_t sml_packed_rows_bytes(int64_t n_rows);
+int sml_pack_rows(const float *tab, const int64_t *ids, int64_t n_rows, int d, void *out, void *stream);
+int sml_fullcat_rank(const void *users_packed, const void *items_packed, const float *s_pos, const int64_t *pos_id, int64_t n_users,
+                     int64_t n_items, int64_t item_id0, int32_t *gt, int32_t *eq, void *stream);
+
 /* ---- row exchange for row-sharded tables (north_star item 4) ---------------------------------
  * Tables are sharded by id (owner = id % world, local row = id / world).  Owner side of the exchange:
  *   sml_gather_pairs : out[n] = [last[loc[n]] | hat[loc[n]]]   (2*d floats per id; answers an id request)

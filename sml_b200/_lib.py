@@ -56,6 +56,9 @@ _PROTOS = {
     "sml_mf_epoch": (_i32, [C.POINTER(StepArgs), _i64, _vp]),
     "sml_tr_epoch": (_i32, [C.POINTER(StepArgs), _i64, _vp]),
     "sml_run_mf_grads": (_i32, [C.POINTER(StepArgs), _vp, _vp, _vp]),
+    "sml_packed_rows_bytes": (_sz, [_i64]),
+    "sml_pack_rows": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "sml_fullcat_rank": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "sml_gather_pairs": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "sml_scatter_grads": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _dbl, _dbl, _vp]),
     "sml_host_rejection_walk": (_i64, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),

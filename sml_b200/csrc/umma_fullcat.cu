@@ -1,0 +1,209 @@
+// Full-catalog evaluation (BASELINE.json north_star item 3, config 5): for every evaluated (user, positive item)
+// pair, the rank of the positive among ALL items of the catalog,
+//     gt[u] = #{i != pos_u : <U_u, I_i> > <U_u, I_pos_u>},   eq[u] = #{i != pos_u : ... == ...},
+// from which recall@K / NDCG@K follow exactly as in the candidate-list evaluation (model/MF.py:59-80 of the
+// reference, which only ever ranks 1 + 999 candidates).  With one positive per row a count is enough: no
+// sort, no top-k selection.
+//
+// This is a [users x 64] x [64 x items] score GEMM whose epilogue is a compare-and-count.  K = 64 is only two
+// 32-wide chunks, so the kernel is epilogue / operand-streaming bound, not MMA bound (hard
+// part 7).  Structure (persistent over the item tiles of one user tile):
+//   * the 128-user A tile (packed 3xTF32 operand, 72 KB) is loaded once per CTA; item tiles (packed, 128 items,
+//     72 KB) stream through a 2-stage cp.async.bulk ring;
+//   * warp 1 issues 24 tcgen05.mma.kind::tf32 per item tile into one of TWO 128-column TMEM accumulators, so the
+//     MMAs of tile j+1 overlap the epilogue of tile j (acc_full / acc_empty mbarriers);
+//   * 8 epilogue warps read the scores with tcgen05.ld (one user row per thread), compare against the row's
+//     positive score and count; the positive's own column is skipped by item id.  Counts accumulate in registers
+//     over all item tiles and leave the SM as one atomicAdd per row.
+// Items can be sharded across GPUs: every rank counts over its shard and the counts are summed (all-reduce).
+#include "sml_common.cuh"
+#include "umma_ptx.cuh"
+
+namespace {
+
+using namespace ptx;
+
+constexpr int FC_THREADS = 320;
+constexpr int FC_STAGES = 2;
+constexpr uint32_t FC_TILE_BYTES = 2 * pk_block_bytes(128);   // 2 K chunks (K = 64), hi + lo: 73 728 B
+constexpr uint32_t FC_SMEM = (1 + FC_STAGES) * FC_TILE_BYTES + 128;
+
+__global__ void __launch_bounds__(FC_THREADS, 1)
+k_fullcat_rank(const uint8_t *__restrict__ Upk, const uint8_t *__restrict__ Ipk, const float *__restrict__ s_pos,
+               const int64_t *__restrict__ pos_id, int64_t n_users, int64_t n_items, int64_t item_id0, int tiles_per_split,
+               int *__restrict__ gt, int *__restrict__ eq) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + FC_TILE_BYTES;
+    uint64_t *a_full = reinterpret_cast<uint64_t *>(smem + (1 + FC_STAGES) * FC_TILE_BYTES);
+    uint64_t *b_full = a_full + 1, *b_empty = b_full + FC_STAGES, *acc_full = b_empty + FC_STAGES, *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_item_tiles = (n_items + 127) / 128;
+    const int64_t t0 = (int64_t)blockIdx.x * tiles_per_split;
+    const int64_t t1 = t0 + tiles_per_split < n_item_tiles ? t0 + tiles_per_split : n_item_tiles;
+    const int ntiles = (int)(t1 - t0);
+    if (ntiles <= 0) return;
+    const int ut = blockIdx.y;
+
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1);
+        for (int i = 0; i < FC_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<256>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(a_full, FC_TILE_BYTES);
+            bulk_g2s(sA, Upk + (size_t)ut * FC_TILE_BYTES, FC_TILE_BYTES, a_full);
+            for (int j = 0; j < ntiles; ++j) {
+                const int s = j % FC_STAGES;
+                if (j >= FC_STAGES) mbar_wait(&b_empty[s], ((j / FC_STAGES) - 1) & 1);
+                mbar_expect_tx(&b_full[s], FC_TILE_BYTES);
+                bulk_g2s(sB + s * FC_TILE_BYTES, Ipk + (size_t)(t0 + j) * FC_TILE_BYTES, FC_TILE_BYTES, &b_full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t IDESC = idesc_tf32(128);
+            mbar_wait(a_full, 0);
+            for (int j = 0; j < ntiles; ++j) {
+                const int s = j % FC_STAGES, acc = j & 1;
+                mbar_wait(&b_full[s], (j / FC_STAGES) & 1);
+                if (j >= 2) mbar_wait(&acc_empty[acc], ((j >> 1) - 1) & 1);          // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t d = tmem + acc * 128;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const uint32_t a_hi = smem_u32(sA) + c * pk_block_bytes(128), a_lo = a_hi + pk_half_bytes(128);
+                    const uint32_t b_hi = smem_u32(sB + s * FC_TILE_BYTES) + c * pk_block_bytes(128), b_lo = b_hi + pk_half_bytes(128);
+#pragma unroll
+                    for (int k = 0; k < PK_BK / 8; ++k) {
+                        const uint32_t ko = k * 2 * PK_LBO;
+                        umma_tf32(d, make_desc(a_lo + ko), make_desc(b_hi + ko), IDESC, (c | k) != 0);
+                        umma_tf32(d, make_desc(a_hi + ko), make_desc(b_lo + ko), IDESC, 1);
+                        umma_tf32(d, make_desc(a_hi + ko), make_desc(b_hi + ko), IDESC, 1);
+                    }
+                }
+                umma_commit(&b_empty[s]);
+                umma_commit(&acc_full[acc]);
+            }
+        }
+    } else {
+        const int quarter = warp & 3, chalf = (warp - 2) >> 2;
+        const int64_t u = (int64_t)ut * 128 + quarter * 32 + lane;
+        const bool live = u < n_users;
+        const float sp = live ? __ldg(s_pos + u) : 0.f;
+        const int64_t pid = live ? __ldg(pos_id + u) : -1;
+        const bool sp_nan = sp != sp;
+        int c_gt = 0, c_eq = 0;
+        for (int j = 0; j < ntiles; ++j) {
+            const int acc = j & 1;
+            mbar_wait(&acc_full[acc], (j >> 1) & 1);
+            tc_fence_after();
+            const int64_t item0 = item_id0 + (t0 + j) * 128;
+#pragma unroll
+            for (int c0 = chalf * 64; c0 < chalf * 64 + 64; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + acc * 128 + c0, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int64_t it = item0 + c0 + i;
+                    const bool ok = (it - item_id0) < n_items && it != pid;
+                    const bool vn = v[i] != v[i];
+                    c_gt += ok && ((v[i] > sp) || (vn && !sp_nan));
+                    c_eq += ok && ((v[i] == sp) || (vn && sp_nan));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+        if (live) {
+            if (c_gt) atomicAdd(gt + u, c_gt);
+            if (c_eq) atomicAdd(eq + u, c_eq);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<256>(tmem);
+}
+
+// rows of a table (optionally gathered by ids) -> packed K-major operand with K = 64 (2 chunks), 128-row tiles
+__global__ void __launch_bounds__(256)
+k_pack_rows(const float *__restrict__ tab, const int64_t *__restrict__ ids, int64_t n, uint8_t *__restrict__ out) {
+    // one 16-lane half-warp per row, lane q owns K quad q (floats 4q..4q+3)
+    const int q = threadIdx.x & 15;
+    const int64_t tiles = (n + 127) / 128;
+    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4; r < tiles * 128; r += ((int64_t)gridDim.x * blockDim.x) >> 4) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < n) {
+            const int64_t id = ids ? __ldg(ids + r) : r;
+            t = __ldg(reinterpret_cast<const float4 *>(tab + id * SML_D) + q);
+        }
+        float h[4], l[4];
+        pk_split(t.x, h[0], l[0]); pk_split(t.y, h[1], l[1]); pk_split(t.z, h[2], l[2]); pk_split(t.w, h[3], l[3]);
+        const int64_t tile = r >> 7;
+        const int rr = (int)(r & 127), k = 4 * q;
+        uint8_t *blk = out + ((size_t)tile * 2 + (k >> 5)) * pk_block_bytes(128) + pk_elem_off(rr, k & 31);
+        *reinterpret_cast<float4 *>(blk) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4 *>(blk + pk_half_bytes(128)) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t sml_packed_rows_bytes(int64_t n_rows) { return (size_t)((n_rows + 127) / 128) * FC_TILE_BYTES; }
+
+int sml_pack_rows(const float *tab, const int64_t *ids, int64_t n_rows, int d, void *out, void *stream) {
+    int rc = sml_check_device();
+    if (rc) return rc;
+    SML_REQUIRE(d == SML_D, SML_E_UNSUPPORTED, "sml_pack_rows: d=%d unsupported (d must be %d)", d, SML_D);
+    if (n_rows <= 0) return SML_OK;
+    SML_REQUIRE(tab && out, SML_E_BADARG, "sml_pack_rows: null pointer");
+    int64_t blocks = ((n_rows + 127) / 128 * 128 * 16 + 255) / 256;
+    const int64_t cap = (int64_t)sml_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    k_pack_rows<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(tab, ids, n_rows, (uint8_t *)out);
+    SML_LAUNCH_OK();
+    return SML_OK;
+}
+
+int sml_fullcat_rank(const void *users_packed, const void *items_packed, const float *s_pos, const int64_t *pos_id, int64_t n_users,
+                     int64_t n_items, int64_t item_id0, int32_t *gt, int32_t *eq, void *stream) {
+    int rc = sml_check_device();
+    if (rc) return rc;
+    if (n_users <= 0 || n_items <= 0) return SML_OK;
+    SML_REQUIRE(users_packed && items_packed && s_pos && pos_id && gt && eq, SML_E_BADARG, "sml_fullcat_rank: null pointer");
+    static bool attr_set = false;
+    if (!attr_set) {
+        SML_CUDA_OK(cudaFuncSetAttribute(k_fullcat_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FC_SMEM));
+        attr_set = true;
+    }
+    const int64_t ut = (n_users + 127) / 128, it = (n_items + 127) / 128;
+    // split the item tiles so that user_tiles x splits covers the SMs a few times over, but keep >= 8 tiles per CTA
+    // to amortise the A-tile load and the pipeline fill
+    const int sms = sml_sm_count();
+    int64_t splits = (4 * sms + ut - 1) / ut;
+    if (splits < 1) splits = 1;
+    if (splits > it) splits = it;
+    int64_t per = (it + splits - 1) / splits;
+    if (per < 8 && it >= 8) per = 8;
+    splits = (it + per - 1) / per;
+    SML_REQUIRE(ut <= 65535, SML_E_UNSUPPORTED, "sml_fullcat_rank: at most 65535*128 users per call (got %lld)", (long long)n_users);
+    dim3 grid((unsigned)splits, (unsigned)ut);
+    k_fullcat_rank<<<grid, FC_THREADS, FC_SMEM, (cudaStream_t)stream>>>((const uint8_t *)users_packed, (const uint8_t *)items_packed, s_pos,
+                                                                        pos_id, n_users, n_items, item_id0, (int)per, gt, eq);
+    SML_LAUNCH_OK();
+    return SML_OK;
+}
+
+}  // extern "C"

@@ -166,6 +166,31 @@ def run_mf_grads(args, d_rows=None, scores=None):
     check(lib().sml_run_mf_grads(C.byref(args), ptr(d_rows), ptr(scores), stream()), "run_mf_grads")
 
 
+def pack_rows(tab, ids=None):
+    """[*, 64] rows (optionally gathered by ids) -> packed tensor-core operand (uint8 tensor)."""
+    n = tab.shape[0] if ids is None else ids.numel()
+    out = torch.empty(int(lib().sml_packed_rows_bytes(n)), dtype=torch.uint8, device=tab.device)
+    check(lib().sml_pack_rows(ptr(_f32(tab, "tab")), ptr(ids), n, tab.shape[1], ptr(out), stream()), "pack_rows")
+    return out
+
+
+def fullcat_ranks(user_tab, item_tab, users, pos_items, items_packed=None, item_id0=0, n_items=None, gt=None, eq=None):
+    """Full-catalog rank counts of (users[n], pos_items[n]) against every row of item_tab (or of a pre-packed
+    item shard).  Returns (gt, eq) int32 [n]; pass gt/eq to accumulate over several item shards."""
+    n = users.numel()
+    s_pos = pair_scores(user_tab, item_tab, users, pos_items) if items_packed is None or item_tab is not None else None
+    up = pack_rows(user_tab, users)
+    if items_packed is None:
+        items_packed = pack_rows(item_tab)
+        n_items = item_tab.shape[0]
+    if gt is None:
+        gt = torch.zeros(n, dtype=torch.int32, device=users.device)
+        eq = torch.zeros(n, dtype=torch.int32, device=users.device)
+    check(lib().sml_fullcat_rank(ptr(up), ptr(items_packed), ptr(s_pos), ptr(_i64(pos_items, "pos_items")), n, n_items, item_id0,
+                                 ptr(gt), ptr(eq), stream()), "fullcat_rank")
+    return gt, eq
+
+
 def gather_pairs(last, hat, loc):
     """Owner side of the row exchange: [n, 128] = [last[loc] | hat[loc]]."""
     n = loc.numel()
