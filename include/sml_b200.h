@@ -210,6 +210,13 @@ int sml_gather_pairs(const float *last, const float *hat, const int64_t *loc, in
 int sml_scatter_grads(float *g, const float *hat, const int64_t *loc, const float *d_rows, int64_t n, int d, double scale,
                       double l2, void *stream);
 
+/* ---- GPU negative sampler (throughput runs; parity runs use the host emulation) ---------------
+ * neg[s] = uniform member of item_all[n_items_all] that is not an interaction of users[s] in this period
+ * (keys = sorted user*span+item), Philox4x32-10, subsequence = s, so results do not depend on the launch shape.
+ * Semantics of offlineDataset_withsample.__getitem__, data/dataset.py:62-71. */
+int sml_philox_negatives(const int64_t *users, int64_t n, const int64_t *item_all, int64_t n_items_all, const int64_t *keys,
+                         int64_t n_keys, int64_t span, uint64_t seed, uint64_t offset, int64_t *neg, void *stream);
+
 /* ---- host helper (all pointers are HOST pointers) ------------------------------------------
  * The sequential walk of offlineDataset_withsample's rejection sampler (data/dataset.py:62-71): sample s
  * takes item_all[draws[p]] for successive p until (users[s], item) is not an interaction of the period

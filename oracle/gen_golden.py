@@ -206,11 +206,11 @@ def gen_eval(ns):
     npz("eval.npz", **out)
 
 
-def gen_period_run(ns, stop=False):
+def gen_period_run(ns, stop=False, news=False):
     """End-to-end meta_train.run on a tiny stream, recording every batch the reference's
     DataLoaders produced so that the CUDA path can replay the same supplied triples."""
     U, I, NP, N, NNEG = 120, 150, 8, 96, 40
-    periods = synth.make_stream(U, I, N, NP, n_neg=NNEG, seed=21)
+    periods = synth.make_stream(U, I, N, NP, n_neg=NNEG, seed=21 + news, churn=0.5 if news else 0.0)
     tmp = tempfile.mkdtemp(prefix="sml_golden_")
     synth.write_stream(tmp + "/", "mini", periods, U, I)
     parser = ns.main_yelp.get_parse()
@@ -219,6 +219,8 @@ def gen_period_run(ns, stop=False):
     args.MF_batch_size = 32; args.TR_batch_size = 16; args.multi_num = 2
     args.MF_epochs = 1; args.TR_epochs = 1; args.pre_model = os.path.join(tmp, "pre.pkl")
     args.TR_stop_ = bool(stop)
+    if news:        # configs[2]: main_news.py settings (MF_epochs=2, TR_epochs=2) on a high-churn stream; data_name != 'yelp'
+        args.data_name = "news"; args.MF_epochs = 2; args.TR_epochs = 2        # takes the other constructor branch (:314-325)
     torch.manual_seed(args.seed); np.random.seed(args.seed + 2)
     pre = ns.MF.MFbasemode(U, I, D)
     torch.save(pre, args.pre_model)
@@ -275,10 +277,10 @@ def gen_period_run(ns, stop=False):
     out["log_kinds"] = np.array([k for k, _ in log])
     for n, (_, rec) in enumerate(log):
         out["log%d" % n] = np.array(rec, dtype=np.int32).reshape(-1, 4)
-    out["args"] = np.array([args.MF_batch_size, args.TR_batch_size, args.multi_num, args.MF_epochs if not stop else 1, args.TR_epochs,
+    out["args"] = np.array([args.MF_batch_size, args.TR_batch_size, args.multi_num, (2 if news else 1), args.TR_epochs,
                             args.seed], dtype=np.int64)
     out["hyper"] = np.array([args.MF_lr, args.l2, args.TR_lr, args.TR_l2], dtype=np.float64)
-    npz("period_run_stop.npz" if stop else "period_run.npz", **out)
+    npz("period_run_news.npz" if news else ("period_run_stop.npz" if stop else "period_run.npz"), **out)
     # restore
     ns.transfer.PreSampleDatast = ns.dataset2.trainDataset_withPreSample
     ns.transfer.SampleDaset = ns.dataset.offlineDataset_withsample
@@ -291,7 +293,8 @@ def main():
     torch.set_num_threads(4)
     ns = ref_harness.load()
     gens = dict(transfer_fwd=gen_transfer_fwd, run_mf=gen_run_mf, mf_steps=gen_mf_steps, tr_steps=gen_tr_steps,
-                eval=gen_eval, period_run=gen_period_run, period_run_stop=lambda n: gen_period_run(n, stop=True))
+                eval=gen_eval, period_run=gen_period_run, period_run_stop=lambda n: gen_period_run(n, stop=True),
+                period_run_news=lambda n: gen_period_run(n, news=True))
     for name, fn in gens.items():
         if a.only and name not in a.only.split(","):
             continue

@@ -96,11 +96,13 @@ class meta_train(object):
     """SML model (reference: model/transfer.py:302-1031)."""
 
     def __init__(self, args, datasets, user_num, item_num, laten_dim, device=None, batch_source=None,
-                 emulate_reference_rng=True):
+                 emulate_reference_rng=True, device_sampler=False):
         """``batch_source``: optional callable (kind, stage_id, epoch, n_rows) -> (user, item, neg) int64
         numpy arrays in batch order; when given it supplies the triples of every epoch (north_star:
         "the same supplied negative-sample indices").  Otherwise triples are drawn like the reference
-        does (``emulate_reference_rng``: same global-RNG consumption as ``--numworkers 0``)."""
+        does (``emulate_reference_rng``: same global-RNG consumption as ``--numworkers 0``).
+        ``device_sampler=True`` (throughput runs): shuffling, pre-sampled column selection and the rejection
+        sampler of the transfer step run on the GPU (Philox), nothing but the period files crosses PCIe."""
         self._require_device(device)
         user_num, item_num = int(user_num), int(item_num)
         if laten_dim != 64:
@@ -112,6 +114,12 @@ class meta_train(object):
                                       "(main_yelp.py:50-55,104) and are not implemented")
         self.batch_source = batch_source
         self.emulate_reference_rng = emulate_reference_rng
+        self.device_sampler = device_sampler
+        self._philox_calls = 0
+        if args.data_name != "yelp":
+            # the reference first builds a throw-away MFbasemode on this branch (model/transfer.py:314-317), which
+            # consumes the global torch generator; mirrored so that batch order stays bit-identical
+            MF.MFbasemode(num_user=user_num, num_item=item_num, laten_factor=laten_dim)
         self.MFbase = load_pre_model(args.pre_model, user_num, item_num, laten_dim, self.device)
 
         self.transfer_type = args.transfer_type
@@ -219,7 +227,26 @@ class meta_train(object):
     def _test_set(self, arr):
         return DeviceTestSet(self._to_device(arr), emulate_reference_rng=self.emulate_reference_rng)
 
+    def _device_triples(self, ds, n_rows):
+        """Whole-epoch triples built on the GPU (device_sampler=True)."""
+        order = torch.randperm(n_rows, device=self.device)
+        if isinstance(ds, PreSampleDatast):
+            d = self._to_device(ds.all_data)
+            col = ds.current_column()
+            ds.advance_epoch()
+            return [d[order, 0].contiguous(), d[order, 1].contiguous(), d[order, col].contiguous()]
+        if not hasattr(ds, "_dev"):
+            T = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(self.device)
+            ds._dev = (T(ds.user), T(ds.item), T(ds.item_all), T(ds._keys))
+        u_all, i_all, item_all, keys = ds._dev
+        u, i = u_all[order].contiguous(), i_all[order].contiguous()
+        self._philox_calls += 1
+        neg = ops.philox_negatives(u, item_all, keys, ds._span, seed=2002, offset=self._philox_calls)
+        return [u, i, neg]
+
     def _triples(self, kind, ds, stage_id, epoch, n_rows):
+        if self.device_sampler and self.batch_source is None:
+            return self._device_triples(ds, n_rows)
         if self.batch_source is not None:
             u, i, j = self.batch_source(kind, stage_id, epoch, n_rows)
             if isinstance(ds, PreSampleDatast):
@@ -465,6 +492,39 @@ class meta_train(object):
         """reference: model/transfer.py:945-959."""
         self.MFbase.user_laten.weight.data.copy_(user_weight)
         self.MFbase.item_laten.weight.data.copy_(item_weight)
+
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self):
+        """Everything a mid-stream resume needs (the reference never saves Adam state):
+        MF tables, the six snapshots, theta, both Adam states and step counters, metric lists, RNG states."""
+        c = lambda t: t.detach().clone()
+        return dict(
+            MFbase=self.MFbase.state_dict(), transfer=self.transfer.state_dict(),
+            snapshots={k: c(getattr(self, k)) for k in ("last_user_weight", "last_item_weight", "user_weight_hat", "item_weight_hat",
+                                                        "last_user_weight_hat", "last_item_weight_hat")},
+            mf_adam={k: c(v) for k, v in self._mf.items()}, mf_adam_state=c(self.MF_optimizer.adam_state),
+            tr_adam={k: c(v) for k, v in self._tr.items()}, tr_adam_state=c(self.transfer_optimizer.adam_state),
+            metrics={k: list(getattr(self, k)) for k in ("recall", "ndcg", "recall_10", "ndcg_10", "recall_5", "ndcg_5", "test_num")},
+            dataset=dict(test_count=getattr(self.dataset, "test_count", 0)),
+            rng=dict(torch=torch.get_rng_state(), numpy=np.random.get_state()), philox_calls=self._philox_calls)
+
+    def load_state_dict(self, sd):
+        self.MFbase.load_state_dict(sd["MFbase"])
+        self.transfer.load_state_dict(sd["transfer"])
+        for k, v in sd["snapshots"].items():
+            getattr(self, k).copy_(v)
+        for k, v in sd["mf_adam"].items():
+            self._mf[k].copy_(v)
+        for k, v in sd["tr_adam"].items():
+            self._tr[k].copy_(v)
+        self.MF_optimizer.adam_state.copy_(sd["mf_adam_state"])
+        self.transfer_optimizer.adam_state.copy_(sd["tr_adam_state"])
+        for k, v in sd["metrics"].items():
+            setattr(self, k, list(v))
+        if hasattr(self.dataset, "test_count"):
+            self.dataset.test_count = sd["dataset"]["test_count"]
+        torch.set_rng_state(sd["rng"]["torch"]); np.random.set_state(sd["rng"]["numpy"])
+        self._philox_calls = sd.get("philox_calls", 0)
 
     # ------------------------------------------------------------------ whole stream
     def run(self, args):

@@ -191,6 +191,15 @@ def fullcat_ranks(user_tab, item_tab, users, pos_items, items_packed=None, item_
     return gt, eq
 
 
+def philox_negatives(users, item_all, keys, span, seed, offset=0):
+    """Device-side rejection sampler (one negative per entry of users); all arguments are int64 CUDA tensors."""
+    neg = torch.empty_like(users)
+    check(lib().sml_philox_negatives(ptr(_i64(users, "users")), users.numel(), ptr(_i64(item_all, "item_all")), item_all.numel(),
+                                     ptr(_i64(keys, "keys")), keys.numel(), int(span), int(seed), int(offset), ptr(neg), stream()),
+          "philox_negatives")
+    return neg
+
+
 def gather_pairs(last, hat, loc):
     """Owner side of the row exchange: [n, 128] = [last[loc] | hat[loc]]."""
     n = loc.numel()

@@ -12,11 +12,11 @@ from tests.test_host_logic import make_args, write_fixture_stream
 pytestmark = pytest.mark.gpu
 
 
-def run_ours(g, tmp, stop, replay):
+def run_ours(g, tmp, stop, replay, news=False):
     from sml_b200.data.dataset2 import transfer_data
     from sml_b200.model.transfer import meta_train
     NP, U, I = write_fixture_stream(g, tmp)
-    args = make_args(g, tmp, stop)
+    args = make_args(g, tmp, stop, news=news)
     torch.manual_seed(args.seed); np.random.seed(args.seed + 2)
     ds = transfer_data(args, path=args.data_path, datasetname="mini", file_path_list=[str(i) for i in range(NP)],
                        test_list=[str(j) for j in range(5, NP)], validation_list=None, online_train_time=2, online_test_time=5)
@@ -43,11 +43,11 @@ def run_ours(g, tmp, stop, replay):
     return meta
 
 
-@pytest.mark.parametrize("name,stop", [("period_run", False), ("period_run_stop", True)])
+@pytest.mark.parametrize("name,stop", [("period_run", False), ("period_run_stop", True), ("period_run_news", False)])
 @pytest.mark.parametrize("replay", [True, False])
 def test_period_run_matches_reference(golden, tmp_path, name, stop, replay):
     g = golden(name)
-    meta = run_ours(g, str(tmp_path), stop, replay)
+    meta = run_ours(g, str(tmp_path), stop, replay, news=name.endswith("news"))
     fu = meta.MFbase.user_laten.weight.data.cpu().numpy()
     fi = meta.MFbase.item_laten.weight.data.cpu().numpy()
     scale = np.abs(g["final_user"]).max()

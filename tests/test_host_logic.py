@@ -17,11 +17,11 @@ from sml_b200.data.dataset2 import transfer_data, trainDataset_withPreSample
 from sml_b200.model.transfer import meta_train
 
 
-def make_args(g, tmp, stop=False):
+def make_args(g, tmp, stop=False, news=False):
     mfb, trb, multi, mfe, tre, seed = (int(x) for x in g["args"])
     lr, l2, trlr, trl2 = (float(x) for x in g["hyper"])
     return argparse.Namespace(
-        data_name="yelp", data_path=tmp + "/", multi_num=multi, MF_lr=lr, MF_epochs=mfe, l2=l2, MF_batch_size=mfb, laten=64,
+        data_name="news" if news else "yelp", data_path=tmp + "/", multi_num=multi, MF_lr=lr, MF_epochs=mfe, l2=l2, MF_batch_size=mfb, laten=64,
         pre_model=os.path.join(tmp, "pre.pt"), MF_sample="all", Load_W_hat=False, clip_grad=False, need_adaptive=False,
         maxnorm_grad=3.0, TR_lr=trlr, TR_l2=trl2, TR_epochs=tre, TR_batch_size=trb, TR_sample_type="alone",
         TR_with_MF_bias=False, TR_stop_=stop, transfer_type="conv_com", seed=seed, numworkers=0, cuda=0, topK=20, pass_num=1,
@@ -67,12 +67,12 @@ class HostProbe(meta_train):
         self.rec.append(("updata",))
 
 
-@pytest.mark.parametrize("name,stop", [("period_run", False), ("period_run_stop", True)])
+@pytest.mark.parametrize("name,stop", [("period_run", False), ("period_run_stop", True), ("period_run_news", False)])
 def test_batch_stream_matches_reference(golden, tmp_path, name, stop):
     g = golden(name)
     tmp = str(tmp_path)
     NP, U, I = write_fixture_stream(g, tmp)
-    args = make_args(g, tmp, stop)
+    args = make_args(g, tmp, stop, news=name.endswith("news"))
     torch.manual_seed(args.seed); np.random.seed(args.seed + 2)       # main_yelp.py:137-140
     ds = transfer_data(args, path=args.data_path, datasetname="mini", file_path_list=[str(i) for i in range(NP)],
                        test_list=[str(j) for j in range(5, NP)], validation_list=None, online_train_time=2, online_test_time=5)
@@ -155,3 +155,23 @@ def test_synth_stream_layout(tmp_path):
         assert len(set(row[2:].tolist())) == 20 and row[1] not in row[2:]
     churn = synth.make_stream(60, 400, 50, 4, n_neg=20, seed=2, churn=0.5)
     assert all(t.shape == (50, 22) for _, t in churn)
+
+
+def test_cli_flags_match_reference():
+    """Flag names and defaults of main_yelp.py:10-120 / main_news.py:8-115 (recorded from the reference's parsers)."""
+    import main_yelp
+    import main_news
+    ref_yelp = {'Lambda_lr': 0.01, 'Load_W_hat': False, 'MF_batch_size': 1024, 'MF_epochs': 1, 'MF_lr': 0.01, 'MF_sample': 'all',
+                'TR_batch_size': 256, 'TR_epochs': 1, 'TR_l2': 0.0001, 'TR_lr': 0.001, 'TR_sample_type': 'alone', 'TR_stop_': False,
+                'TR_with_MF_bias': False, 'clip_grad': False, 'cuda': 0, 'data_name': 'yelp', 'data_path': '/home/sml/dataset/',
+                'l2': 1e-06, 'laten': 64, 'maxnorm_grad': 3.0, 'min_l2': 0.0001, 'multi_num': 10, 'need_adaptive': False,
+                'need_writer': False, 'norm': False, 'numworkers': 4, 'pass_num': 1,
+                'pre_model': '/home/sml/save_model/sml/yelp/BCE_init.pkl', 'seed': 2000, 'set_t_as_tt': False,
+                'test_in_TR_Train': False, 'topK': 20, 'tqdm': False, 'transfer_type': 'conv_com'}
+    ref_news = dict(ref_yelp, MF_epochs=2, TR_epochs=2, multi_num=7, data_name='news', pre_model='/home/sml/save_model/sml/news/BCE_init.pkl')
+    for mod, ref in ((main_yelp, ref_yelp), (main_news, ref_news)):
+        got = vars(mod.get_parse().parse_args([]))
+        for k, v in ref.items():
+            assert got[k] == v, (mod.__name__, k, got[k], v)
+    a = main_yelp.get_parse().parse_args(["--MF_epochs=3", "--TR_stop_", "yes"])
+    assert a.MF_epochs == 3 and a.TR_stop_ is True
