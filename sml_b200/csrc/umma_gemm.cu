@@ -240,7 +240,12 @@ k_umma_gemm(UmmaParams P) {
                 for (int k = 0; k < UM_BK / 8; ++k) {
                     const uint32_t ko = k * 2 * UM_LBO;                          // one MMA = K 8 = two core matrices
                     const uint64_t ah = make_desc(a_hi + ko), al = make_desc(a_lo + ko), bh = make_desc(b_hi + ko), bl = make_desc(b_lo + ko);
+#ifdef SML_4XTF32
+                    umma_tf32(tmem, al, bl, IDESC, (c | k) != 0);
+                    umma_tf32(tmem, al, bh, IDESC, 1);
+#else
                     umma_tf32(tmem, al, bh, IDESC, (c | k) != 0);                // small terms first
+#endif
                     umma_tf32(tmem, ah, bl, IDESC, 1);
                     umma_tf32(tmem, ah, bh, IDESC, 1);
                 }

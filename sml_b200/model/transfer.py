@@ -499,7 +499,8 @@ class meta_train(object):
         MF tables, the six snapshots, theta, both Adam states and step counters, metric lists, RNG states."""
         c = lambda t: t.detach().clone()
         return dict(
-            MFbase=self.MFbase.state_dict(), transfer=self.transfer.state_dict(),
+            MFbase={k: c(v) for k, v in self.MFbase.state_dict().items()},
+            transfer={k: c(v) for k, v in self.transfer.state_dict().items()},
             snapshots={k: c(getattr(self, k)) for k in ("last_user_weight", "last_item_weight", "user_weight_hat", "item_weight_hat",
                                                         "last_user_weight_hat", "last_item_weight_hat")},
             mf_adam={k: c(v) for k, v in self._mf.items()}, mf_adam_state=c(self.MF_optimizer.adam_state),
