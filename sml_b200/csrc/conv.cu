@@ -368,7 +368,8 @@ int sml_launch_conv_bwd(const SmlConvBwdGroup *groups, int n_groups, int variant
     if (max_n == 0) return SML_OK;
     // fewer, fatter CTAs when parameter gradients are reduced (one atomic flush per CTA)
     int gx = grid_for_rows(max_n);
-    if (theta) { const int cap = sml_sm_count(); if (gx > cap) gx = cap; }
+    // each CTA ends with 95 global atomics onto the same 95 parameters: a few dozen CTAs per group keep that cheap
+    if (theta) { const int cap = 32; if (gx > cap) gx = cap; }
     dim3 grid(gx, n_groups);
 #define SML_CB(R_, MODE_, TH_) k_conv_bwd<R_, MODE_, TH_><<<grid, CONV_THREADS, 0, st>>>(P, dA, l2, d_rows)
     const bool com = variant == SML_VARIANT_COM;

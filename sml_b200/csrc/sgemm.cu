@@ -103,25 +103,30 @@ k_sgemm(GemmParams P) {
     }
 }
 
-// out[c] += sum_r X[r, c]; one CTA per 32 columns, 8 row-lanes, fixed-order tree.
+// out[c] += sum_r X[r, c].  Grid = (column groups of 32, problems, row slices): each CTA reduces 8 row lanes of
+// its slice in a fixed order and adds one partial per column with an fp32 atomic (bias gradients).
 struct ColsumParams { SmlColsumProb p[MAX_PROBS]; };
+constexpr int COLSUM_SLICES = 16;
 
 __global__ void __launch_bounds__(256) k_colsum(ColsumParams P) {
     __shared__ float s[8][33];
     const SmlColsumProb p = P.p[blockIdx.y];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     if (blockIdx.x * 32 >= p.cols) return;
+    const int per = (p.rows + COLSUM_SLICES - 1) / COLSUM_SLICES;
+    const int r0 = blockIdx.z * per, r1 = min(p.rows, r0 + per);
+    if (r0 >= r1) return;
     const int rl = threadIdx.x >> 5;
     float a = 0.f;
     if (c < p.cols)
-        for (int r = rl; r < p.rows; r += 8) a += p.X[(size_t)r * p.ld + c];
+        for (int r = r0 + rl; r < r1; r += 8) a += p.X[(size_t)r * p.ld + c];
     s[rl][threadIdx.x & 31] = a;
     __syncthreads();
     if (rl == 0 && c < p.cols) {
         float t = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) t += s[i][threadIdx.x & 31];
-        p.out[c] += t;
+        atomicAdd(p.out + c, t);
     }
 }
 
@@ -171,7 +176,7 @@ int sml_launch_colsum(const SmlColsumProb *probs, int n_probs, cudaStream_t st) 
     int maxc = 0;
     for (int i = 0; i < n_probs; ++i) { P.p[i] = probs[i]; if (probs[i].cols > maxc) maxc = probs[i].cols; }
     if (maxc == 0) return SML_OK;
-    dim3 grid((maxc + 31) / 32, n_probs);
+    dim3 grid((maxc + 31) / 32, n_probs, COLSUM_SLICES);
     k_colsum<<<grid, 256, 0, st>>>(P);
     SML_LAUNCH_OK();
     return SML_OK;
