@@ -39,6 +39,7 @@ HYPER = dict(multi_num=10, MF_epochs=1, TR_epochs=1, MF_batch_size=1024, TR_batc
 EVAL_BYTES_PER_ROW = (1 + 1000) * 256 + 1001 * 8          # 264 264 B per test row
 TRANSFER_FLOP_PER_ROW = 403456
 TRANSFER_BYTES_PER_ROW = 768
+EVAL_NCU_DRAM_BYTES = 655_940_000                          # dram__bytes_read.sum + dram__bytes_write.sum of one 75 000-row launch (ncu --set full, r01)
 
 
 def make_args(**over):
@@ -367,8 +368,10 @@ def run_ours(a):
         "phase_counts_per_period": {k: v[0] / K for k, v in phases.items()},
         "kernels": kern,
         "roofline": {"kernel": "k_eval_candidates", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
-                     "note": "algorithmic bytes = 264264 B x rows per launch; the 31 MB item table is L2 resident so frac can exceed 1"},
+                     "frac": ach / hbm_peak, "traffic": EVAL_NCU_DRAM_BYTES if shape["rows"] == 75000 else None, "peak_source": peak_src,
+                     "note": "algorithmic bytes = 264264 B x rows per launch (19.8 GB); the 31 MB item table is L2 resident "
+                             "(ncu: L2 hit 95%, DRAM traffic 0.66 GB per launch = the 600 MB id file + tables, profiles/r01_kernels_ncu.md), "
+                             "so frac exceeds 1: the kernel runs at the L2->SM limit (~6300 B/clk x 1.965 GHz = 12.4 TB/s)"},
     }
     if rank == 0:
         if world == 1 and not a.no_cpu_baseline:

@@ -139,7 +139,7 @@ struct SmlPkProb {
     uint8_t *Cpk;         // packed output = A operand of the next GEMM (K = N), or null
     int c_tile0;
 };
-int sml_launch_umma_packed(const SmlPkProb *probs, int n_probs, int epi, cudaStream_t st);
+int sml_launch_umma_packed(const SmlPkProb *probs, int n_probs, int epi, cudaStream_t st, int ksplit = 1);
 // packed weight operands of the nets: per net SML_PK_THETA_BYTES
 constexpr size_t SML_PK_OFF_P1 = 0;            // W1   as B[512][320], 128-row blocks (fc1 forward)
 constexpr size_t SML_PK_OFF_P2 = 1474560;      // W2   as B[64][512],   64-row blocks (fc2 forward)

@@ -54,10 +54,10 @@ StepWs carve(void *ws, int64_t B) {
     w.partials = (float *)take(3 * 1024 * sizeof(float));
     w.A = (float *)take(R * 320 * sizeof(float));
     w.Z1 = (float *)take(R * 512 * sizeof(float));
-    w.Y = (float *)take(R * 64 * sizeof(float));
+    w.Y = (float *)take(R * 64 * sizeof(float));          // Y and dA are adjacent: one memset clears both when the
+    w.dA = (float *)take(R * 320 * sizeof(float));        // split-K GEMMs accumulate into them
     w.dY = (float *)take(R * 64 * sizeof(float));
     w.dZ1 = (float *)take(R * 512 * sizeof(float));
-    w.dA = (float *)take(R * 320 * sizeof(float));
     w.rowsq = (float *)take(R * sizeof(float));
     w.Apk = (uint8_t *)take(T * 10 * pk_block_bytes(128));
     w.Gpk = (uint8_t *)take(T * 16 * pk_block_bytes(128));
@@ -92,6 +92,10 @@ void make_groups(const sml_step_args *a, SmlRowGroup g[3]) {
     g[2] = SmlRowGroup{a->last_item, a->hat_item, a->neg, ti, r.B, r.Bp + r.B, pitch};
 }
 
+// K = 512 GEMMs (fc2, d1) of small batches have only a handful of output tiles: slice K so they cover more SMs
+// (measured: 119.3 -> 117.0 us for the B = 256 transfer step; at B = 1024 the atomics cost more than the slicing gains)
+int step_ksplit(const Rows &r) { return (r.user_tiles + r.item_tiles) <= 12 ? 4 : 1; }
+
 // two-net problem pair for the packed GEMMs
 void pk_pair(SmlPkProb out[2], const Rows &r, const uint8_t *A, int KC, size_t w_off, int N, const float *theta, size_t bias_off,
              const float *aux, float *C, int ldc, uint8_t *Cpk, const uint8_t *theta_pk) {
@@ -123,6 +127,8 @@ int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, b
         rc = sml_launch_pack_theta(a->theta, w.theta_pk, 2, st);
         if (rc) return rc;
     }
+    if (tc && step_ksplit(r) > 1)      // split-K slices accumulate into Y and dA
+        SML_CUDA_OK(cudaMemsetAsync(w.Y, 0, (size_t)((char *)w.dY - (char *)w.Y), st));
     rc = sml_launch_conv_fwd(g, 3, a->variant, (!tc || need_plain_A) ? w.A : nullptr, tc ? w.Apk : nullptr,
                              want_rowsq ? w.rowsq : nullptr, st);
     if (rc) return rc;
@@ -134,7 +140,7 @@ int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, b
         if (rc) return rc;
         // fc2: Y = GELU(Z1) W2^T + b2 (:48-49)
         pk_pair(p, r, w.Gpk, 16, SML_PK_OFF_P2, 64, a->theta, SML_OFF_F2B, nullptr, w.Y, 64, nullptr, w.theta_pk);
-        rc = sml_launch_umma_packed(p, 2, SML_PK_FC2, st);
+        rc = sml_launch_umma_packed(p, 2, SML_PK_FC2, st, step_ksplit(r));
         if (rc) return rc;
     } else {
         SmlGemmProb fc1[2] = {
@@ -169,7 +175,7 @@ int fc1_dgrad(const sml_step_args *a, const StepWs &w, cudaStream_t st) {
     if (sml_use_tensor_cores()) {
         SmlPkProb p[2];
         pk_pair(p, r, w.dZpk, 16, SML_PK_OFF_P4, 320, a->theta, 0, nullptr, w.dA, 320, nullptr, w.theta_pk);
-        return sml_launch_umma_packed(p, 2, SML_PK_D1, st);
+        return sml_launch_umma_packed(p, 2, SML_PK_D1, st, step_ksplit(r));
     }
     const float *tu = a->theta, *ti = a->theta + SML_NET_STRIDE;
     SmlGemmProb d1[2] = {

@@ -25,7 +25,7 @@ constexpr int PKG_EPI_THREADS = 256;
 constexpr int PKG_STAGES = 3;
 constexpr int PKG_MAX_PROBS = 4;
 
-struct PkParams { SmlPkProb p[PKG_MAX_PROBS]; };
+struct PkParams { SmlPkProb p[PKG_MAX_PROBS]; int ksplit; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -89,9 +89,17 @@ __global__ void __launch_bounds__(PKG_THREADS, 1)
 k_umma_packed(PkParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     using S = PkSmem<BN>;
-    const SmlPkProb p = P.p[blockIdx.z];
+    // split-K: blockIdx.z = problem * ksplit + slice.  A single CTA streaming K = 512 pulls 0.6 MB through one SM's
+    // L2 port (~7 us); slicing K spreads that over more SMs.  Slices add their partial tile with fp32 atomics into a
+    // pre-zeroed C (plain-output epilogues only); slice 0 adds the bias.
+    const SmlPkProb p = P.p[blockIdx.z / P.ksplit];
+    const int ks = blockIdx.z % P.ksplit;
     const int tile_m = blockIdx.y, tile_n = blockIdx.x;
     if (tile_m >= p.m_tiles || tile_n * BN >= p.N) return;                    // nothing allocated yet
+    const int c_per = (p.KC + P.ksplit - 1) / P.ksplit;
+    const int c_beg = ks * c_per, c_end = (c_beg + c_per < p.KC) ? c_beg + c_per : p.KC;
+    if (c_beg >= c_end) return;
+    const bool split = P.ksplit > 1;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + S::TOTAL - 64);
     uint64_t *empty = full + PKG_STAGES;
     uint64_t *done = empty + PKG_STAGES;
@@ -117,9 +125,9 @@ k_umma_packed(PkParams P) {
         if (lane == 0) {
             const uint8_t *a = p.A + (size_t)(p.a_tile0 + tile_m) * KC * S::A_BYTES;
             const uint8_t *b = p.B + (size_t)tile_n * KC * S::B_BYTES;
-            for (int c = 0; c < KC; ++c) {
-                const int s = c % PKG_STAGES;
-                if (c >= PKG_STAGES) mbar_wait(&empty[s], ((c / PKG_STAGES) - 1) & 1);
+            for (int c = c_beg; c < c_end; ++c) {
+                const int i = c - c_beg, s = i % PKG_STAGES;
+                if (i >= PKG_STAGES) mbar_wait(&empty[s], ((i / PKG_STAGES) - 1) & 1);
                 uint8_t *st = smem + s * S::STAGE;
                 mbar_expect_tx(&full[s], S::STAGE);
                 bulk_g2s(st, a + (size_t)c * S::A_BYTES, S::A_BYTES, &full[s]);
@@ -129,7 +137,7 @@ k_umma_packed(PkParams P) {
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            for (int c = 0; c < KC; ++c) {
+            for (int c = 0; c < c_end - c_beg; ++c) {
                 const int s = c % PKG_STAGES;
                 mbar_wait(&full[s], (c / PKG_STAGES) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -163,7 +171,7 @@ k_umma_packed(PkParams P) {
             float v[32];
             tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + c0, v);
             const int nb = n0 + c0;
-            if (EPI == SML_PK_FC1 || EPI == SML_PK_FC2) {
+            if ((EPI == SML_PK_FC1 || EPI == SML_PK_FC2) && ks == 0) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + nb) + q);
@@ -181,9 +189,14 @@ k_umma_packed(PkParams P) {
             }
             if (p.C && valid) {
                 // a thread writes 128 contiguous bytes of its row (the row pitch separates the lanes)
-                float4 *dst = reinterpret_cast<float4 *>(p.C + m * p.ldc + nb);
+                if (split) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    for (int i = 0; i < 32; ++i) atomicAdd(p.C + m * p.ldc + nb + i, v[i]);
+                } else {
+                    float4 *dst = reinterpret_cast<float4 *>(p.C + m * p.ldc + nb);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                }
             }
             if ((EPI == SML_PK_FC1 || EPI == SML_PK_D2) && p.Cpk) {
                 // column nb.. of this GEMM = K index of the next one: one 32-wide K chunk, 8 quads; lanes r%8
@@ -261,9 +274,12 @@ int launch_pk(const PkParams &P, dim3 grid, cudaStream_t st) {
 
 }  // namespace
 
-int sml_launch_umma_packed(const SmlPkProb *probs, int n_probs, int epi, cudaStream_t st) {
+int sml_launch_umma_packed(const SmlPkProb *probs, int n_probs, int epi, cudaStream_t st, int ksplit) {
     SML_REQUIRE(n_probs >= 1 && n_probs <= PKG_MAX_PROBS, SML_E_BADARG, "packed gemm: bad problem count %d", n_probs);
+    SML_REQUIRE(ksplit >= 1 && (ksplit == 1 || epi == SML_PK_FC2 || epi == SML_PK_D1), SML_E_BADARG,
+                "packed gemm: split-K only for the plain-output epilogues (fc2, d1)");
     PkParams P;
+    P.ksplit = ksplit;
     int max_mt = 0;
     const int N = probs[0].N;
     for (int i = 0; i < n_probs; ++i) {
@@ -274,9 +290,9 @@ int sml_launch_umma_packed(const SmlPkProb *probs, int n_probs, int epi, cudaStr
     if (max_mt == 0) return SML_OK;
     switch (epi) {
         case SML_PK_FC1: SML_REQUIRE(N % 128 == 0, SML_E_BADARG, "packed gemm: fc1 N"); return launch_pk<128, SML_PK_FC1>(P, dim3(N / 128, max_mt, n_probs), st);
-        case SML_PK_FC2: SML_REQUIRE(N % 64 == 0, SML_E_BADARG, "packed gemm: fc2 N"); return launch_pk<64, SML_PK_FC2>(P, dim3(N / 64, max_mt, n_probs), st);
+        case SML_PK_FC2: SML_REQUIRE(N % 64 == 0, SML_E_BADARG, "packed gemm: fc2 N"); return launch_pk<64, SML_PK_FC2>(P, dim3(N / 64, max_mt, n_probs * ksplit), st);
         case SML_PK_D2: SML_REQUIRE(N % 128 == 0, SML_E_BADARG, "packed gemm: d2 N"); return launch_pk<128, SML_PK_D2>(P, dim3(N / 128, max_mt, n_probs), st);
-        case SML_PK_D1: SML_REQUIRE(N % 64 == 0, SML_E_BADARG, "packed gemm: d1 N"); return launch_pk<64, SML_PK_D1>(P, dim3(N / 64, max_mt, n_probs), st);
+        case SML_PK_D1: SML_REQUIRE(N % 64 == 0, SML_E_BADARG, "packed gemm: d1 N"); return launch_pk<64, SML_PK_D1>(P, dim3(N / 64, max_mt, n_probs * ksplit), st);
     }
     sml_set_error("packed gemm: bad epilogue %d", epi);
     return SML_E_BADARG;
