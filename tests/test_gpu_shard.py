@@ -46,7 +46,7 @@ def test_sharded_steps_world1_match_fused_steps():
     ops.tr_step(a)
     lt = s.tr_step(T(ids[0], dev), T(ids[1], dev), T(ids[2], dev))
     assert abs(float(lt) - loss[0].item()) < 2e-5
-    assert (m2.theta - m1.theta).abs().max().item() < 1e-5
+    assert (m2.theta - m1.theta).abs().max().item() < 1e-4        # after Adam: step tolerance (atomic summation order varies)
     # updata + evaluation on the shard
     s.updata()
     rows = T(np.concatenate([rng.integers(0, U, (64, 1)), rng.integers(0, I, (64, 30))], 1).astype(np.int64), dev)
