@@ -36,6 +36,7 @@ constexpr int UM_STAGES = 3;
 constexpr uint32_t UM_LBO = 144;           // bytes between K-adjacent core matrices
 constexpr uint32_t UM_SBO = 8 * UM_LBO;    // bytes between 8-row groups (1152)
 constexpr int UM_MAX_PROBS = 4;
+constexpr int UM_NACC = 4;                 // independent TMEM accumulators the K chunks are dealt to
 
 struct UmmaParams { SmlGemmProb p[UM_MAX_PROBS]; int transpose_out; int ksplit; };
 
@@ -215,7 +216,7 @@ k_umma_gemm(UmmaParams P) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN * UM_NACC) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -240,14 +241,12 @@ k_umma_gemm(UmmaParams P) {
                 for (int k = 0; k < UM_BK / 8; ++k) {
                     const uint32_t ko = k * 2 * UM_LBO;                          // one MMA = K 8 = two core matrices
                     const uint64_t ah = make_desc(a_hi + ko), al = make_desc(a_lo + ko), bh = make_desc(b_hi + ko), bl = make_desc(b_lo + ko);
-#ifdef SML_4XTF32
-                    umma_tf32(tmem, al, bl, IDESC, (c | k) != 0);
-                    umma_tf32(tmem, al, bh, IDESC, 1);
-#else
-                    umma_tf32(tmem, al, bh, IDESC, (c | k) != 0);                // small terms first
-#endif
-                    umma_tf32(tmem, ah, bl, IDESC, 1);
-                    umma_tf32(tmem, ah, bh, IDESC, 1);
+                    // K chunks alternate over UM_NACC accumulators (see umma_packed.cu: the tensor core's fp32 adder
+                    // truncates, so short accumulation chains summed in the epilogue are more accurate)
+                    const uint32_t d = tmem + (uint32_t)(c % UM_NACC) * BN;
+                    umma_tf32(d, al, bh, IDESC, (c >= UM_NACC) || (k != 0));     // small terms first; first MMA overwrites
+                    umma_tf32(d, ah, bl, IDESC, 1);
+                    umma_tf32(d, ah, bh, IDESC, 1);
                 }
                 umma_commit(&empty[s]);                                          // stage reusable once these MMAs retire
             }
@@ -302,13 +301,19 @@ k_umma_gemm(UmmaParams P) {
     for (int c0 = (warp >> 2) * (BN / 2); c0 < (warp >> 2) * (BN / 2) + BN / 2; c0 += 32) {
         float v[32];
         tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0, v);
+        for (int a = 1; a < (nchunks < UM_NACC ? nchunks : UM_NACC); ++a) {
+            float w[32];
+            tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + a * BN + c0, w);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += w[i];
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) epi[row * (BN + 1) + c0 + i] = v[i];
     }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN) : "memory");
+    if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN * UM_NACC) : "memory");
     if (!P.transpose_out) {
         // coalesced rows: a warp writes 32 consecutive n of one m
         for (int idx = threadIdx.x; idx < UM_BM * BN; idx += UM_CTA_THREADS) {
