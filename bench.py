@@ -113,39 +113,45 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------------
 # CPU port (cpu_baseline leg and --impl reference)
 # --------------------------------------------------------------------------------------------
-def cpu_port_periods_per_s(shape, seed=0, scale=1.0, verbose=False):
+def cpu_port_periods_per_s(shape, seed=0, scale=1.0, verbose=False, device="cpu"):
     """Times oracle/torch_port.Port on a bounded sample of one Yelp-shaped period and composes the
-    per-unit times into one period (counts from period_counts)."""
+    per-unit times into one period (counts from period_counts).  device="cuda" runs the same stock-PyTorch
+    operator sequence on the GPU (the reference's own torch-CUDA path)."""
     import torch
     from oracle import sml_oracle as O
     from oracle.torch_port import Port
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    gpu = device != "cpu"
+    if gpu:
+        torch.backends.cudnn.allow_tf32 = False        # SURVEY 8c shim (5): fp32 convs like the CPU path
+        torch.backends.cuda.matmul.allow_tf32 = False
+    sync = (lambda: torch.cuda.synchronize()) if gpu else (lambda: None)
     rng = np.random.default_rng(seed)
     U, I, R = shape["n_users"], shape["n_items"], shape["rows"]
     user0 = rng.standard_normal((U, 64), dtype=np.float32); item0 = rng.standard_normal((I, 64), dtype=np.float32)
     p = Port(user0, item0, O.init_theta(np.random.default_rng(1)), O.init_theta(np.random.default_rng(2)),
-             mf_lr=HYPER["MF_lr"], l2=HYPER["l2"], tr_lr=HYPER["TR_lr"], tr_l2=HYPER["TR_l2"])
+             mf_lr=HYPER["MF_lr"], l2=HYPER["l2"], tr_lr=HYPER["TR_lr"], tr_l2=HYPER["TR_l2"], device=device)
     n_mf, n_tr = max(2, int(24 * scale)), max(4, int(80 * scale))
     n_up, n_ev = int(min(U, 49152 * scale)), int(6144 * scale)
     Bm, Bt = HYPER["MF_batch_size"], HYPER["TR_batch_size"]
     ids = lambda B: (rng.integers(0, U, B), rng.integers(0, I, B), rng.integers(0, I, B))
     rows = np.concatenate([rng.integers(0, U, (n_ev, 1)), rng.integers(0, I, (n_ev, 1000))], 1)
-    p.mf_step(*ids(Bm)); p.tr_step(*ids(Bt))                      # warm-up (allocator, thread pool)
+    p.mf_step(*ids(Bm)); p.tr_step(*ids(Bt)); sync()              # warm-up (allocator, thread pool)
     t = time.perf_counter()
     for _ in range(n_mf):
         p.mf_step(*ids(Bm))
-    t_mf = (time.perf_counter() - t) / n_mf
+    sync(); t_mf = (time.perf_counter() - t) / n_mf
     t = time.perf_counter()
     for _ in range(n_tr):
         p.tr_step(*ids(Bt))
-    t_tr = (time.perf_counter() - t) / n_tr
+    sync(); t_tr = (time.perf_counter() - t) / n_tr
     t = time.perf_counter()
     n_rows_up = p.updata(max_rows=n_up)
-    t_up_row = (time.perf_counter() - t) / n_rows_up
+    sync(); t_up_row = (time.perf_counter() - t) / n_rows_up
     t = time.perf_counter()
     p.test_model(rows, HYPER["topK"])
-    t_ev_row = (time.perf_counter() - t) / n_ev
+    sync(); t_ev_row = (time.perf_counter() - t) / n_ev
     mf_steps, tr_steps, n_updata, n_evals = period_counts(R)
     t_period = mf_steps * t_mf + tr_steps * t_tr + n_updata * (U + I) * t_up_row + n_evals * R * t_ev_row
     sample = ("%d MF steps (B=%d, dense Adam on %dx64+%dx64), %d TR steps (B=%d), transfer of %d rows, candidate eval of %d rows "
@@ -377,6 +383,10 @@ def run_ours(a):
         if world == 1 and not a.no_cpu_baseline:
             v, cores, sample, detail = cpu_port_periods_per_s(YELP, seed=0, scale=1.0)
             out["cpu_baseline"] = {"value": v, "unit": "periods/s", "cores": cores, "kind": "port", "sample": sample, "detail": detail}
+            # second bar: the same stock-PyTorch operator sequence on this B200 (cuBLAS / cuDNN / ATen)
+            v2, _, sample2, detail2 = cpu_port_periods_per_s(YELP, seed=0, scale=4.0, device="cuda")
+            out["torch_cuda_baseline"] = {"value": v2, "unit": "periods/s", "kind": "port (stock PyTorch eager on the same GPU, TF32 off)",
+                                          "sample": sample2, "detail": detail2}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

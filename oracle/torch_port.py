@@ -51,10 +51,13 @@ def run_mf(user_net, item_net, ul, uh, il, ih, jl, jh):         # conv_transfer.
 class Port(object):
     """State of one SML run on the CPU: MF tables (nn.Embedding, dense Adam), snapshots, two nets."""
 
-    def __init__(self, user0, item0, theta_user, theta_item, mf_lr=0.01, l2=1e-6, tr_lr=0.001, tr_l2=1e-4):
-        self.user = torch.nn.Embedding.from_pretrained(torch.as_tensor(np.array(user0)), freeze=False)
-        self.item = torch.nn.Embedding.from_pretrained(torch.as_tensor(np.array(item0)), freeze=False)
-        self.user_net, self.item_net = Net(theta_user), Net(theta_item)
+    def __init__(self, user0, item0, theta_user, theta_item, mf_lr=0.01, l2=1e-6, tr_lr=0.001, tr_l2=1e-4, device="cpu"):
+        """device="cuda": the same stock-PyTorch operator sequence on the GPU (cuBLAS / cuDNN / ATen kernels, TF32 off) --
+        the "existing Blackwell implementation" bar of BASELINE.md section 3."""
+        self.device = torch.device(device)
+        self.user = torch.nn.Embedding.from_pretrained(torch.as_tensor(np.array(user0)), freeze=False).to(self.device)
+        self.item = torch.nn.Embedding.from_pretrained(torch.as_tensor(np.array(item0)), freeze=False).to(self.device)
+        self.user_net, self.item_net = Net(theta_user).to(self.device), Net(theta_item).to(self.device)
         self.last_user = self.user.weight.data.clone(); self.last_item = self.item.weight.data.clone()
         self.user_hat = self.user.weight.data.clone(); self.item_hat = self.item.weight.data.clone()
         self.mf_opt = torch.optim.Adam([self.user.weight, self.item.weight], lr=mf_lr, weight_decay=0)
@@ -62,7 +65,7 @@ class Port(object):
         self.l2 = l2
 
     def mf_step(self, u, i, j):                                 # model/transfer.py:463-511
-        u, i, j = (torch.as_tensor(x).long() for x in (u, i, j))
+        u, i, j = (torch.as_tensor(x).long().to(self.device) for x in (u, i, j))
         self.mf_opt.zero_grad(); self.tr_opt.zero_grad()
         wu, wi, wj = self.user(u), self.item(i), self.item(j)
         loss = run_mf(self.user_net, self.item_net, self.last_user[u], wu, self.last_item[i], wi, self.last_item[j], wj)
@@ -72,7 +75,7 @@ class Port(object):
         return float(loss.detach())
 
     def tr_step(self, u, i, j):                                 # model/transfer.py:701-728
-        u, i, j = (torch.as_tensor(x).long() for x in (u, i, j))
+        u, i, j = (torch.as_tensor(x).long().to(self.device) for x in (u, i, j))
         self.tr_opt.zero_grad()
         loss = run_mf(self.user_net, self.item_net, self.last_user[u], self.user_hat[u], self.last_item[i], self.item_hat[i],
                       self.last_item[j], self.item_hat[j])
@@ -96,7 +99,7 @@ class Port(object):
 
     @torch.no_grad()
     def test(self, rows, topK):                                 # model/MF.py:45-80
-        rows = torch.as_tensor(rows).long()
+        rows = torch.as_tensor(rows).long().to(self.device)
         ue = self.user(rows[:, 0]).unsqueeze(1)
         sc = torch.mul(ue, self.item(rows[:, 1:])).sum(-1)
         _, rank = torch.topk(sc, topK)
