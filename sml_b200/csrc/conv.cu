@@ -238,8 +238,12 @@ constexpr int LOSS_WARPS = LOSS_THREADS / 32;
 __global__ void __launch_bounds__(LOSS_THREADS)
 k_loss(const float *__restrict__ Y, const float *__restrict__ rowsq, int64_t B, int64_t rowP, int64_t rowN, int loss_kind,
        int normalize_user, float l2, float *__restrict__ dY, uint8_t *__restrict__ dYpk, float *__restrict__ scores,
-       float *__restrict__ loss_out, float *__restrict__ partials, unsigned int *__restrict__ ticket) {
+       float *__restrict__ loss_out, float *__restrict__ partials, unsigned int *__restrict__ ticket,
+       float *__restrict__ gb_user, float *__restrict__ gb_item) {
     __shared__ float s_part[LOSS_WARPS][3];
+    __shared__ float s_gb[2][SML_D];
+    float gbu[2] = {0.f, 0.f}, gbi[2] = {0.f, 0.f};          // fc2 bias gradients: column sums of dY (this thread's 2 columns)
+    if (gb_user && threadIdx.x < 2 * SML_D) s_gb[threadIdx.x / SML_D][threadIdx.x % SML_D] = 0.f;
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float acc_pos = 0.f, acc_neg = 0.f, acc_sq = 0.f;   // lane 0 only
@@ -278,6 +282,7 @@ k_loss(const float *__restrict__ Y, const float *__restrict__ rowsq, int64_t B, 
             for (int h = 0; h < 2; ++h) {
                 const int k = lane + 32 * h;
                 const float du = (dsp * i_[h] + dsn * j_[h]) * inv_n, di = dsp * u[h], dj = dsn * u[h];
+                gbu[h] += du; gbi[h] += di + dj;
                 dY[b * SML_D + k] = du;
                 dY[(rowP + b) * SML_D + k] = di;
                 dY[(rowN + b) * SML_D + k] = dj;
@@ -291,6 +296,13 @@ k_loss(const float *__restrict__ Y, const float *__restrict__ rowsq, int64_t B, 
     }
     if (lane == 0) { s_part[w][0] = acc_pos; s_part[w][1] = acc_neg; s_part[w][2] = acc_sq; }
     __syncthreads();
+    if (gb_user) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) { atomicAdd(&s_gb[0][lane + 32 * h], gbu[h]); atomicAdd(&s_gb[1][lane + 32 * h], gbi[h]); }
+        __syncthreads();
+        if (threadIdx.x < SML_D) atomicAdd(gb_user + threadIdx.x, s_gb[0][threadIdx.x]);
+        else if (threadIdx.x < 2 * SML_D) atomicAdd(gb_item + threadIdx.x - SML_D, s_gb[1][threadIdx.x - SML_D]);
+    }
     if (threadIdx.x == 0) {
         float p = 0.f, n = 0.f, q = 0.f;
         for (int i = 0; i < LOSS_WARPS; ++i) { p += s_part[i][0]; n += s_part[i][1]; q += s_part[i][2]; }
@@ -387,11 +399,11 @@ int sml_launch_conv_bwd(const SmlConvBwdGroup *groups, int n_groups, int variant
 
 int sml_launch_loss(const float *Y, const float *rowsq, int64_t B, int64_t row_pos, int64_t row_neg, int loss_kind,
                     int normalize_user, float l2, float *dY, uint8_t *dYpk, float *scores, float *loss_out, float *partials,
-                    unsigned int *ticket, cudaStream_t st) {
+                    unsigned int *ticket, cudaStream_t st, float *gb_user, float *gb_item) {
     int64_t blocks = (B + LOSS_WARPS - 1) / LOSS_WARPS;
     if (blocks > 1024) blocks = 1024;   // partials[] holds 3 * 1024 floats
     k_loss<<<(int)blocks, LOSS_THREADS, 0, st>>>(Y, rowsq, B, row_pos, row_neg, loss_kind, normalize_user, l2, dY, dYpk, scores,
-                                                 loss_out, partials, ticket);
+                                                 loss_out, partials, ticket, gb_user, gb_item);
     SML_LAUNCH_OK();
     return SML_OK;
 }

@@ -117,9 +117,10 @@ int sml_launch_colsum(const SmlColsumProb *probs, int n_probs, cudaStream_t st);
 
 // loss + dY.  Rows of Y / dY / rowsq: user b at b, positive item at row_pos + b, negative at row_neg + b.
 // dYpk (optional): dY additionally as a packed tensor-core operand (K = 64).
+// gb_user / gb_item (optional): += column sums of dY over the user rows / the item rows (fc2 bias gradients)
 int sml_launch_loss(const float *Y, const float *rowsq, int64_t B, int64_t row_pos, int64_t row_neg, int loss_kind,
                     int normalize_user, float l2, float *dY, uint8_t *dYpk, float *scores, float *loss_out, float *partials,
-                    unsigned int *ticket, cudaStream_t st);
+                    unsigned int *ticket, cudaStream_t st, float *gb_user = nullptr, float *gb_item = nullptr);
 
 // tcgen05 GEMM with pre-packed operands (umma_packed.cu)
 enum { SML_PK_FC1 = 0, SML_PK_FC2 = 1, SML_PK_D2 = 2, SML_PK_D1 = 3 };
@@ -138,6 +139,7 @@ struct SmlPkProb {
     int ldc;
     uint8_t *Cpk;         // packed output = A operand of the next GEMM (K = N), or null
     int c_tile0;
+    float *colsum;        // d2 only: += column sums of the valid output rows (fc1 bias gradient), or null
 };
 int sml_launch_umma_packed(const SmlPkProb *probs, int n_probs, int epi, cudaStream_t st, int ksplit = 1);
 // packed weight operands of the nets: per net SML_PK_THETA_BYTES
@@ -146,6 +148,7 @@ constexpr size_t SML_PK_OFF_P2 = 1474560;      // W2   as B[64][512],   64-row b
 constexpr size_t SML_PK_OFF_P3 = 1769472;      // W2^T as B[512][64],  128-row blocks (dZ1 = dY W2)
 constexpr size_t SML_PK_OFF_P4 = 2064384;      // W1^T as B[320][512],  64-row blocks (dA = dZ1 W1)
 constexpr size_t SML_PK_THETA_BYTES = 3538944;
-int sml_launch_pack_theta(const float *theta, uint8_t *out, int n_nets, cudaStream_t st);
+// adam_state != null: also performs the step's Adam tick (betas 0.9 / 0.999) inside the same launch
+int sml_launch_pack_theta(const float *theta, uint8_t *out, int n_nets, cudaStream_t st, int64_t *adam_state = nullptr, double lr = 0.0);
 
 int sml_launch_row_normalize(float *Y, int64_t n, cudaStream_t st);

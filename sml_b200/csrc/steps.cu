@@ -108,14 +108,16 @@ void pk_pair(SmlPkProb out[2], const Rows &r, const uint8_t *A, int KC, size_t w
         p.M = (int)(net ? 2 * r.B : r.B);
         p.N = N;
         p.bias = bias_off ? theta + (size_t)net * SML_NET_STRIDE + bias_off : nullptr;
-        p.aux = aux; p.C = C; p.ldc = ldc; p.Cpk = Cpk; p.c_tile0 = p.a_tile0;
+        p.aux = aux; p.C = C; p.ldc = ldc; p.Cpk = Cpk; p.c_tile0 = p.a_tile0; p.colsum = nullptr;
     }
 }
 
 // forward through fc2 + loss + data gradients down to dZ1 (shared by all step flavours).
 // need_plain_A: the transfer step's fc1 weight gradient reads A.
+// g_theta != null (tensor-core path): the fc2 / fc1 bias gradients are accumulated by the loss kernel and by the d2
+// epilogue.  tick_state != null: the Adam tick rides in the theta packer's launch.
 int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, bool need_plain_A, bool pack_theta, float l2,
-                     float *scores, cudaStream_t st) {
+                     float *scores, cudaStream_t st, float *g_theta = nullptr, int64_t *tick_state = nullptr, double tick_lr = 0.0) {
     const Rows r = rows_of(a->batch);
     const int64_t B = r.B;
     const float *tu = a->theta, *ti = a->theta + SML_NET_STRIDE;
@@ -124,9 +126,13 @@ int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, b
     make_groups(a, g);
     int rc;
     if (tc && pack_theta) {
-        rc = sml_launch_pack_theta(a->theta, w.theta_pk, 2, st);
+        rc = sml_launch_pack_theta(a->theta, w.theta_pk, 2, st, tick_state, tick_lr);
+        if (rc) return rc;
+    } else if (tick_state) {
+        rc = sml_adam_tick(tick_state, tick_lr, 0.9, 0.999, st);
         if (rc) return rc;
     }
+    float *gbu2 = (tc && g_theta) ? g_theta + SML_OFF_F2B : nullptr, *gbi2 = (tc && g_theta) ? g_theta + SML_NET_STRIDE + SML_OFF_F2B : nullptr;
     if (tc && step_ksplit(r) > 1)      // split-K slices accumulate into Y and dA
         SML_CUDA_OK(cudaMemsetAsync(w.Y, 0, (size_t)((char *)w.dY - (char *)w.Y), st));
     rc = sml_launch_conv_fwd(g, 3, a->variant, (!tc || need_plain_A) ? w.A : nullptr, tc ? w.Apk : nullptr,
@@ -155,12 +161,13 @@ int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, b
         if (rc) return rc;
     }
     rc = sml_launch_loss(w.Y, want_rowsq ? w.rowsq : nullptr, B, r.Bp, r.Bp + B, a->loss, a->variant == SML_VARIANT_CONV, l2, w.dY,
-                         tc ? w.dYpk : nullptr, scores, a->loss_out, w.partials, w.ticket, st);
+                         tc ? w.dYpk : nullptr, scores, a->loss_out, w.partials, w.ticket, st, gbu2, gbi2);
     if (rc) return rc;
     // dZ1 = (dY W2) * GELU'(Z1)
     if (tc) {
         SmlPkProb p[2];
         pk_pair(p, r, w.dYpk, 2, SML_PK_OFF_P3, 512, a->theta, 0, w.Z1, w.dZ1, 512, w.dZpk, w.theta_pk);
+        if (g_theta) { p[0].colsum = g_theta + SML_OFF_F1B; p[1].colsum = g_theta + SML_NET_STRIDE + SML_OFF_F1B; }
         return sml_launch_umma_packed(p, 2, SML_PK_D2, st);
     }
     SmlGemmProb d2[2] = {
@@ -212,6 +219,7 @@ int fc_wgrads(const sml_step_args *a, const StepWs &w, float *g_theta, cudaStrea
     if (sml_use_tensor_cores()) rc = sml_launch_umma_gemm(w1, 2, SML_A_KM, SML_B_KN, SML_EPI_ACCUM, 0, 64, st, ksplit > 2 ? ksplit / 2 : 1);
     else rc = sml_launch_sgemm(w1, 2, SML_A_KM, SML_B_KN, SML_EPI_ACCUM, st);
     if (rc) return rc;
+    if (sml_use_tensor_cores()) return SML_OK;     // bias gradients already accumulated by k_loss and the d2 epilogue
     SmlColsumProb cs[4] = {{w.dY, gu + SML_OFF_F2B, (int)B, 64, 64},
                            {w.dY + Bp * 64, gi + SML_OFF_F2B, (int)(2 * B), 64, 64},
                            {w.dZ1, gu + SML_OFF_F1B, (int)B, 512, 512},
@@ -305,10 +313,10 @@ int sml_transfer_fwd(const float *x_t, const float *x_hat, const int64_t *ids, i
         if (rc) return rc;
         if (tc) {
             const int tiles = (int)(up128(n) / 128);
-            SmlPkProb f1 = {Apk, theta_pk + SML_PK_OFF_P1, 10, tiles, 0, 0, (int)n, 512, theta_net + SML_OFF_F1B, nullptr, nullptr, 512, Gpk, 0};
+            SmlPkProb f1 = {Apk, theta_pk + SML_PK_OFF_P1, 10, tiles, 0, 0, (int)n, 512, theta_net + SML_OFF_F1B, nullptr, nullptr, 512, Gpk, 0, nullptr};
             rc = sml_launch_umma_packed(&f1, 1, SML_PK_FC1, st);
             if (rc) return rc;
-            SmlPkProb f2 = {Gpk, theta_pk + SML_PK_OFF_P2, 16, tiles, 0, 0, (int)n, 64, theta_net + SML_OFF_F2B, nullptr, out + r0 * SML_D, 64, nullptr, 0};
+            SmlPkProb f2 = {Gpk, theta_pk + SML_PK_OFF_P2, 16, tiles, 0, 0, (int)n, 64, theta_net + SML_OFF_F2B, nullptr, out + r0 * SML_D, 64, nullptr, 0, nullptr};
             rc = sml_launch_umma_packed(&f2, 1, SML_PK_FC2, st);
             if (rc) return rc;
         } else {
@@ -338,9 +346,7 @@ int sml_tr_step(const sml_step_args *a, void *stream) {
     SML_REQUIRE(a->g_theta && a->m_theta && a->v_theta && a->adam_state, SML_E_BADARG, "sml_tr_step: null theta-gradient / Adam-state pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const StepWs w = carve(a->workspace, a->batch);
-    rc = sml_adam_tick(a->adam_state, a->lr, 0.9, 0.999, stream);
-    if (rc) return rc;
-    rc = forward_and_loss(a, w, false, true, true, 0.f, nullptr, st);      // theta changes every step: re-pack
+    rc = forward_and_loss(a, w, false, true, true, 0.f, nullptr, st, a->g_theta, a->adam_state, a->lr);   // theta changes every step: re-pack
     if (rc) return rc;
     rc = fc_wgrads(a, w, a->g_theta, st);
     if (rc) return rc;
@@ -364,7 +370,7 @@ int sml_run_mf_grads(const sml_step_args *a, float *d_rows, float *scores, void 
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const StepWs w = carve(a->workspace, a->batch);
-    rc = forward_and_loss(a, w, false, a->g_theta != nullptr, true, 0.f, scores, st);
+    rc = forward_and_loss(a, w, false, a->g_theta != nullptr, true, 0.f, scores, st, a->g_theta);
     if (rc) return rc;
     if (a->g_theta) {
         rc = fc_wgrads(a, w, a->g_theta, st);

@@ -202,6 +202,24 @@ k_umma_packed(PkParams P) {
                     v[4 * q + 2] *= sml_gelu_grad(z.z); v[4 * q + 3] *= sml_gelu_grad(z.w);
                 }
             }
+            if (EPI == SML_PK_D2 && p.colsum) {
+                // fc1 bias gradient = column sums of dZ1: transpose-reduce the warp's 32 rows x 32 columns with 31
+                // shuffles (lane l ends with the sum of column l), one atomicAdd per lane
+                float t[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) t[i] = valid ? v[i] : 0.f;
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const bool up = (lane & off) != 0;
+#pragma unroll
+                    for (int i = 0; i < off; ++i) {
+                        const float send = up ? t[i] : t[i + off];
+                        const float keep = up ? t[i + off] : t[i];
+                        t[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
+                }
+                atomicAdd(p.colsum + nb + lane, t[0]);
+            }
             if (p.C && valid) {
                 // a thread writes 128 contiguous bytes of its row (the row pitch separates the lanes)
                 if (split) {
@@ -240,7 +258,16 @@ k_umma_packed(PkParams P) {
 // ---- theta packer ---------------------------------------------------------------------------------
 // The four weight operands of one net, split and packed:  P1 = W1 as B[n=512][k=320] (128-row blocks),
 // P2 = W2 as B[64][512] (64-row), P3 = W2^T as B[512][64] (128-row), P4 = W1^T as B[320][512] (64-row).
-__global__ void __launch_bounds__(256) k_pack_theta(const float *__restrict__ theta, uint8_t *__restrict__ out, int n_nets) {
+__global__ void __launch_bounds__(256) k_pack_theta(const float *__restrict__ theta, uint8_t *__restrict__ out, int n_nets,
+                                                    int64_t *adam_state, double lr) {
+    if (adam_state && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        // the step's Adam tick (sml_adam_tick) rides along: step counter + step_size + sqrt(bias_correction2)
+        const int64_t t = adam_state[0] + 1;
+        adam_state[0] = t;
+        float *f = reinterpret_cast<float *>(adam_state + 1);
+        f[0] = (float)(lr / (1.0 - pow(0.9, (double)t)));
+        f[1] = (float)sqrt(1.0 - pow(0.999, (double)t));
+    }
     const int net = blockIdx.y >> 2, which = blockIdx.y & 3;
     if (net >= n_nets) return;
     const float *th = theta + (size_t)net * SML_NET_STRIDE;
@@ -313,9 +340,9 @@ int sml_launch_umma_packed(const SmlPkProb *probs, int n_probs, int epi, cudaStr
     return SML_E_BADARG;
 }
 
-int sml_launch_pack_theta(const float *theta, uint8_t *out, int n_nets, cudaStream_t st) {
+int sml_launch_pack_theta(const float *theta, uint8_t *out, int n_nets, cudaStream_t st, int64_t *adam_state, double lr) {
     dim3 grid(40, 4 * n_nets);
-    k_pack_theta<<<grid, 256, 0, st>>>(theta, out, n_nets);
+    k_pack_theta<<<grid, 256, 0, st>>>(theta, out, n_nets, adam_state, lr);
     SML_LAUNCH_OK();
     return SML_OK;
 }

@@ -186,6 +186,8 @@ class meta_train(object):
         self._graphs = {}
         self._graph_warm = set()
         self.graph_launches = 0                    # kernels executed through graph replays (not seen by sml_launch_count)
+        self._tab_version = 0                      # bumped by every method that writes the MF tables
+        self._eval_cache = None
         self.events = EventTimers(False)           # CUDA-event phase timers (bench.py switches them on)
 
         self.recall = []
@@ -272,8 +274,18 @@ class meta_train(object):
 
     def _eval(self, test_set, topK):
         t0 = time.perf_counter()
+        # The reference re-scores a file even when nothing changed since its last evaluation (the "before train MF" pass
+        # of outer phase p+1 repeats the last pass of phase p, model/transfer.py:445 vs :740).  The scoring pass is reused
+        # when the same file is evaluated again and no method of this class has touched the MF tables in between
+        # (_tab_version); the reference's RNG draw per evaluation is still consumed inside test_model.
+        if isinstance(test_set, DeviceTestSet):
+            key = (test_set.rows.data_ptr(), test_set.rows.shape, self._tab_version)
+            if self._eval_cache is not None and self._eval_cache[0] == key:
+                test_set._rank_cache, test_set.frozen = self._eval_cache[1], True
         with self.events("eval"):
             r = test_model(self.MFbase, test_set, topK=topK)
+        if isinstance(test_set, DeviceTestSet) and test_set._rank_cache is not None:
+            self._eval_cache = ((test_set.rows.data_ptr(), test_set.rows.shape, self._tab_version), test_set._rank_cache)
         self.timers["eval"] += time.perf_counter() - t0
         return r
 
@@ -337,6 +349,7 @@ class meta_train(object):
                                       loss=ops.LOSS_BCE if self.transfer.variant == ops.VARIANT_COM else ops.LOSS_BPR,
                                       adam_state=self.MF_optimizer.adam_state, lr=lr, l2=args.l2, loss_out=self._loss,
                                       workspace=ws, **self._mf)
+        self._tab_version += 1
         self._run_epoch("mf", build, (user, item, neg), n, B, (lr, args.l2, uw.data_ptr(), iw.data_ptr()))
         return self._loss[1].item() / nb
 
@@ -503,6 +516,7 @@ class meta_train(object):
         """w_t = Transfer(w_{t-1}, w_hat) for EVERY row of both tables, written straight into the
         MFbase tables (reference: model/transfer.py:884-902 + load_MFbase_weight)."""
         t0 = time.perf_counter()
+        self._tab_version += 1
         self.MFbase.eval()
         self.transfer.eval()
         if self.transfer_type != "transfer2":
@@ -531,6 +545,7 @@ class meta_train(object):
 
     def load_MFbase_weight(self, user_weight, item_weight):
         """reference: model/transfer.py:945-959."""
+        self._tab_version += 1
         self.MFbase.user_laten.weight.data.copy_(user_weight)
         self.MFbase.item_laten.weight.data.copy_(item_weight)
 
@@ -551,6 +566,7 @@ class meta_train(object):
             rng=dict(torch=torch.get_rng_state(), numpy=np.random.get_state()), philox_calls=self._philox_calls)
 
     def load_state_dict(self, sd):
+        self._tab_version += 1
         self.MFbase.load_state_dict(sd["MFbase"])
         self.transfer.load_state_dict(sd["transfer"])
         for k, v in sd["snapshots"].items():
