@@ -114,6 +114,28 @@ void pk_pair(SmlPkProb out[2], const Rows &r, const uint8_t *A, int KC, size_t w
 
 // forward through fc2 + loss + data gradients down to dZ1 (shared by all step flavours).
 // need_plain_A: the transfer step's fc1 weight gradient reads A.
+// Fork / join helper: the two weight-gradient GEMMs of the transfer step only feed the final Adam update, so they run
+// on a library-owned side stream concurrently with dA = dZ1 W1 and the conv backward (both ~25 us at B = 256).  Event
+// record / wait are stream-capturable, so inside a CUDA graph this becomes two parallel branches.
+struct SideStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, join2 = nullptr;
+};
+SideStream *side_stream() {
+    static SideStream per_dev[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SideStream &x = per_dev[dev];
+    if (!x.s) {
+        if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&x.fork2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&x.join2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    return &x;
+}
+
 // g_theta != null (tensor-core path): the fc2 / fc1 bias gradients are accumulated by the loss kernel and by the d2
 // epilogue.  tick_state != null: the Adam tick rides in the theta packer's launch.
 int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, bool need_plain_A, bool pack_theta, float l2,
@@ -125,7 +147,14 @@ int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, b
     SmlRowGroup g[3];
     make_groups(a, g);
     int rc;
-    if (tc && pack_theta) {
+    SideStream *ss = (tc && pack_theta && tick_state) ? side_stream() : nullptr;   // transfer step: pack theta || conv prologue
+    if (ss) {
+        SML_CUDA_OK(cudaEventRecord(ss->fork2, st));
+        SML_CUDA_OK(cudaStreamWaitEvent(ss->s, ss->fork2, 0));
+        rc = sml_launch_pack_theta(a->theta, w.theta_pk, 2, ss->s, tick_state, tick_lr);
+        if (rc) return rc;
+        SML_CUDA_OK(cudaEventRecord(ss->join2, ss->s));
+    } else if (tc && pack_theta) {
         rc = sml_launch_pack_theta(a->theta, w.theta_pk, 2, st, tick_state, tick_lr);
         if (rc) return rc;
     } else if (tick_state) {
@@ -138,6 +167,7 @@ int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, b
     rc = sml_launch_conv_fwd(g, 3, a->variant, (!tc || need_plain_A) ? w.A : nullptr, tc ? w.Apk : nullptr,
                              want_rowsq ? w.rowsq : nullptr, st);
     if (rc) return rc;
+    if (ss) SML_CUDA_OK(cudaStreamWaitEvent(st, ss->join2, 0));
     if (tc) {
         SmlPkProb p[2];
         // fc1: Z1 = A W1^T + b1 (conv_transfer.py:47); also emits GELU(Z1) packed for fc2
@@ -166,7 +196,8 @@ int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, b
     // dZ1 = (dY W2) * GELU'(Z1)
     if (tc) {
         SmlPkProb p[2];
-        pk_pair(p, r, w.dYpk, 2, SML_PK_OFF_P3, 512, a->theta, 0, w.Z1, w.dZ1, 512, w.dZpk, w.theta_pk);
+        // plain dZ1 is only read by the weight gradients (transfer step); the MF step keeps just the packed copy
+        pk_pair(p, r, w.dYpk, 2, SML_PK_OFF_P3, 512, a->theta, 0, w.Z1, need_plain_A ? w.dZ1 : nullptr, 512, w.dZpk, w.theta_pk);
         if (g_theta) { p[0].colsum = g_theta + SML_OFF_F1B; p[1].colsum = g_theta + SML_NET_STRIDE + SML_OFF_F1B; }
         return sml_launch_umma_packed(p, 2, SML_PK_D2, st);
     }
@@ -348,9 +379,14 @@ int sml_tr_step(const sml_step_args *a, void *stream) {
     const StepWs w = carve(a->workspace, a->batch);
     rc = forward_and_loss(a, w, false, true, true, 0.f, nullptr, st, a->g_theta, a->adam_state, a->lr);   // theta changes every step: re-pack
     if (rc) return rc;
-    rc = fc_wgrads(a, w, a->g_theta, st);
+    SideStream *ss = side_stream();
+    SML_REQUIRE(ss, SML_E_CUDA, "sml_tr_step: could not create the side stream");
+    SML_CUDA_OK(cudaEventRecord(ss->fork, st));
+    SML_CUDA_OK(cudaStreamWaitEvent(ss->s, ss->fork, 0));
+    rc = fc_wgrads(a, w, a->g_theta, ss->s);                               // branch 1: dW2, dW1 (+ bias sums on the SIMT path)
     if (rc) return rc;
-    rc = fc1_dgrad(a, w, st);
+    SML_CUDA_OK(cudaEventRecord(ss->join, ss->s));
+    rc = fc1_dgrad(a, w, st);                                              // branch 2: dA, conv backward
     if (rc) return rc;
     SmlRowGroup g[3];
     make_groups(a, g);
@@ -358,6 +394,7 @@ int sml_tr_step(const sml_step_args *a, void *stream) {
     SmlConvBwdGroup bg[3] = {{g[0], nullptr, gu}, {g[1], nullptr, gi}, {g[2], nullptr, gi}};
     rc = sml_launch_conv_bwd(bg, 3, a->variant, w.dA, 0.f, nullptr, st);
     if (rc) return rc;
+    SML_CUDA_OK(cudaStreamWaitEvent(st, ss->join, 0));
     // Adam with coupled L2 (weight_decay = TR_l2, model/transfer.py:393) over the whole theta block
     return sml_adam_dense(a->theta, a->m_theta, a->v_theta, a->g_theta, 2 * (int64_t)SML_NET_STRIDE, a->adam_state, 0.9, 0.999,
                           1e-8, a->l2, 1, stream);
