@@ -228,13 +228,14 @@ def run_ours(a):
     sys.stdout = quiet                                   # the drop-in prints like the reference; keep the JSON line clean
     try:
         # ---------------- e2e arm: host arrays, H2D/D2H inside the timed region ----------------
-        e2e_s, e2e_h2d, e2e_d2h = float("nan"), 0, 0
-        mf_steps, tr_steps, n_updata, n_evals = period_counts(shape["rows"])
-        if not a.skip_e2e:
-            pin = lambda x: torch.from_numpy(x).pin_memory().numpy()          # inputs live in pinned host memory
+        def e2e_arm(device_sampler):
+            """K periods through meta_train.train_one_stage3 with pinned HOST period files; nothing is resident when a
+            period starts, H2D of the files / triples and D2H of every loss and metric are inside the timed region."""
+            pin = lambda x: torch.from_numpy(x).pin_memory().numpy()
             e2e_periods = [(pin(tr), pin(te)) for tr, te in periods[:W + K + 1]]
             ds = MemoryStream(e2e_periods, U, I)
-            meta = meta_train(args, ds, U, I, 64, device=dev)
+            torch.manual_seed(args.seed + rank); np.random.seed(args.seed + 2 + rank)
+            meta = meta_train(args, ds, U, I, 64, device=dev, device_sampler=device_sampler, emulate_reference_rng=not device_sampler)
             h2d = [0]
             orig_to_device, orig_upload = meta._to_device, meta._upload
 
@@ -244,7 +245,7 @@ def run_ours(a):
                 return orig_to_device(arr)
 
             def upload(arrs):
-                h2d[0] += sum(int(np.asarray(x).size) * 8 for x in arrs)
+                h2d[0] += sum(int(np.asarray(x).size) * 8 for x in arrs if not isinstance(x, torch.Tensor))
                 return orig_upload(arrs)
             meta._to_device, meta._upload = to_device, upload
             stage = 0
@@ -260,13 +261,17 @@ def run_ours(a):
                 meta._dev_cache.clear()                      # nothing of this period is resident when its step starts
                 meta.train_one_stage3(args, stage); stage += 1
             torch.cuda.synchronize()
-            e2e_s = time.perf_counter() - t0
-            mf_steps, tr_steps, n_updata, n_evals = period_counts(shape["rows"])
-            e2e_h2d = h2d[0] / K
-            e2e_d2h = (n_evals * 8 + (HYPER["multi_num"] * (HYPER["MF_epochs"] + HYPER["TR_epochs"])) * 4)
+            secs = time.perf_counter() - t0
             if world > 1:
-                t = torch.tensor([e2e_s], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t)
-            del meta, e2e_periods
+                t = torch.tensor([secs], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); secs = float(t)
+            return secs, h2d[0] / K
+
+        e2e_s, e2e_h2d, e2e_parity_s, e2e_parity_h2d = float("nan"), 0, float("nan"), 0
+        mf_steps, tr_steps, n_updata, n_evals = period_counts(shape["rows"])
+        e2e_d2h = (n_evals * 8 + (HYPER["multi_num"] * (HYPER["MF_epochs"] + HYPER["TR_epochs"])) * 4)
+        if not a.skip_e2e:
+            e2e_s, e2e_h2d = e2e_arm(True)                   # throughput mode: batches sampled on the GPU (Philox)
+            e2e_parity_s, e2e_parity_h2d = e2e_arm(False)    # parity mode: the reference's RNG streams reproduced on the host
 
         # ---------------- resident arm: everything in HBM before the clock starts ----------------
         res_periods = periods[W + K:]
@@ -367,7 +372,10 @@ def run_ours(a):
                    "parallelism": "1 replica stream per GPU" if world > 1 else "single GPU"},
         "samples_per_s": world * K * (HYPER["multi_num"] * shape["rows"] * (HYPER["MF_epochs"] + HYPER["TR_epochs"])) / dev_s,
         "e2e": {"value": (world * K / e2e_s) if e2e_s == e2e_s else None, "unit": "periods/s", "h2d_bytes_per_step": int(e2e_h2d),
-                "d2h_bytes_per_step": int(e2e_d2h)},
+                "d2h_bytes_per_step": int(e2e_d2h), "mode": "meta_train(device_sampler=True): host period files, batches sampled on the GPU"},
+        "e2e_parity_mode": {"value": (world * K / e2e_parity_s) if e2e_parity_s == e2e_parity_s else None, "unit": "periods/s",
+                            "h2d_bytes_per_step": int(e2e_parity_h2d), "d2h_bytes_per_step": int(e2e_d2h),
+                            "mode": "meta_train default: batches drawn on the host bit-identically to the reference (--numworkers 0)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "phases_ms_per_period": {k: v[1] / K for k, v in phases.items()},
