@@ -67,15 +67,6 @@ _PROTOS = {
     "sml_plain_mf_grads": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 
-# optional entry points (added by later kernels); bound when present, required by their callers
-_OPTIONAL = {
-    "sml_umma_selftest": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
-    "sml_transfer_fwd_tc": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),
-    "sml_transfer_fwd_tc_workspace_bytes": (_sz, [_i64]),
-    "sml_score_topk": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
-    "sml_score_topk_workspace_bytes": (_sz, [_i64, _i64, _i32]),
-}
-
 _lib = None
 
 
@@ -92,10 +83,6 @@ def lib():
     for name, (res, args) in _PROTOS.items():
         fn = getattr(l, name)        # AttributeError => stale library; fail loudly
         fn.restype, fn.argtypes = res, args
-    for name, (res, args) in _OPTIONAL.items():
-        if hasattr(l, name):
-            fn = getattr(l, name)
-            fn.restype, fn.argtypes = res, args
     if l.sml_abi_version() != ABI_VERSION:
         raise RuntimeError("sml_b200: ABI mismatch: library %d, python %d" % (l.sml_abi_version(), ABI_VERSION))
     _lib = l

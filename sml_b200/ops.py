@@ -73,19 +73,15 @@ def _workspace(nbytes, device, tag):
 
 
 def transfer_forward(x_t, x_hat, theta_net, variant=VARIANT_COM, ids=None, normalize_out=False, out=None, tensor_cores=None):
-    """out[n] = one_transfer(stack(x_t[i_n], x_hat[i_n])), i_n = ids[n] or n.  theta_net: flat fp32 [NET_STRIDE]."""
+    """out[n] = one_transfer(stack(x_t[i_n], x_hat[i_n])), i_n = ids[n] or n.  theta_net: flat fp32 [NET_STRIDE].
+    (``tensor_cores`` is ignored: the GEMM path is a process-wide choice, SML_GEMM=simt in the environment.)"""
     _f32(x_t, "x_t"); _f32(x_hat, "x_hat"); _f32(theta_net, "theta_net")
     n = x_t.shape[0] if ids is None else ids.numel()
     if out is None:
         out = torch.empty(n, D, dtype=torch.float32, device=x_t.device)
     l = lib()
-    use_tc = hasattr(l, "sml_transfer_fwd_tc") if tensor_cores is None else bool(tensor_cores)
-    if use_tc:
-        ws = _workspace(l.sml_transfer_fwd_tc_workspace_bytes(n), x_t.device, "fwd_tc")
-        fn = l.sml_transfer_fwd_tc
-    else:
-        ws = _workspace(l.sml_transfer_fwd_workspace_bytes(n), x_t.device, "fwd")
-        fn = l.sml_transfer_fwd
+    ws = _workspace(l.sml_transfer_fwd_workspace_bytes(n), x_t.device, "fwd")
+    fn = l.sml_transfer_fwd
     check(fn(ptr(x_t), ptr(x_hat), ptr(ids), n, x_t.shape[1], variant, ptr(theta_net), int(bool(normalize_out)), ptr(out),
              ptr(ws), ws.numel(), stream()), "transfer_fwd")
     return out

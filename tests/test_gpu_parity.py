@@ -130,9 +130,8 @@ def test_transfer_forward_vs_oracle(dev, n):
     th = O.init_theta(np.random.default_rng(3))
     flat = flat_theta(th, dev)
     xt = rng.standard_normal((n, 64)).astype(np.float32); xh = (0.5 * rng.standard_normal((n, 64))).astype(np.float32)
-    for tc in (False,) + ((True,) if hasattr(ops.lib(), "sml_transfer_fwd_tc") else ()):
-        y = ops.transfer_forward(T(xt, dev), T(xh, dev), flat, tensor_cores=tc).cpu().numpy()
-        assert rel_err(y, O.conv_transfer_com_forward(th, xt, xh)) < FWD_TOL, tc
+    y = ops.transfer_forward(T(xt, dev), T(xh, dev), flat).cpu().numpy()
+    assert rel_err(y, O.conv_transfer_com_forward(th, xt, xh)) < FWD_TOL
     ids = rng.integers(0, n, size=max(1, n // 2)).astype(np.int64)
     y = ops.transfer_forward(T(xt, dev), T(xh, dev), flat, ids=T(ids, dev)).cpu().numpy()
     assert rel_err(y, O.conv_transfer_com_forward(th, xt[ids], xh[ids])) < FWD_TOL
