@@ -13,6 +13,8 @@
 namespace {
 
 __global__ void k_adam_tick(int64_t *state, double lr, double beta1, double beta2) {
+    sml_pdl_wait();
+    sml_pdl_trigger();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         const int64_t t = state[0] + 1;
         state[0] = t;
@@ -37,6 +39,8 @@ template <bool ZERO>
 __global__ void __launch_bounds__(256)
 k_adam_dense(float4 *__restrict__ p, float4 *__restrict__ m, float4 *__restrict__ v, float4 *__restrict__ g, int64_t n4,
              const int64_t *__restrict__ state, float b1c, float beta2, float b2c, float eps, float wd) {
+    sml_pdl_wait();
+    sml_pdl_trigger();
     // b1c = (float)(1 - beta1), b2c = (float)(1 - beta2) are rounded from the double differences on the
     // host, as torch does (1.0f - 0.999f would be off by 5e-5 relative)
     const float *f = reinterpret_cast<const float *>(state + 1);
@@ -61,7 +65,7 @@ int sml_adam_tick(int64_t *state, double lr, double beta1, double beta2, void *s
     int rc = sml_check_device();
     if (rc) return rc;
     SML_REQUIRE(state, SML_E_BADARG, "sml_adam_tick: null state");
-    k_adam_tick<<<1, 32, 0, (cudaStream_t)stream>>>(state, lr, beta1, beta2);
+    SML_CUDA_OK(sml_launch(k_adam_tick, dim3(1), dim3(32), 0, (cudaStream_t)stream, state, lr, beta1, beta2));
     SML_LAUNCH_OK();
     return SML_OK;
 }
@@ -80,13 +84,11 @@ int sml_adam_dense(float *p, float *m, float *v, float *g, int64_t n, const int6
     const int64_t cap = (int64_t)sml_sm_count() * 8;
     if (blocks > cap) blocks = cap;
     if (zero_grad)
-        k_adam_dense<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((float4 *)p, (float4 *)m, (float4 *)v, (float4 *)g, n4,
-                                                                           state, (float)(1.0 - beta1), (float)beta2,
-                                                                           (float)(1.0 - beta2), (float)eps, (float)weight_decay);
+        SML_CUDA_OK(sml_launch(k_adam_dense<true>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (float4 *)p, (float4 *)m, (float4 *)v, (float4 *)g, n4,
+                               state, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps, (float)weight_decay));
     else
-        k_adam_dense<false><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((float4 *)p, (float4 *)m, (float4 *)v, (float4 *)g, n4,
-                                                                            state, (float)(1.0 - beta1), (float)beta2,
-                                                                            (float)(1.0 - beta2), (float)eps, (float)weight_decay);
+        SML_CUDA_OK(sml_launch(k_adam_dense<false>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (float4 *)p, (float4 *)m, (float4 *)v, (float4 *)g, n4,
+                               state, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps, (float)weight_decay));
     SML_LAUNCH_OK();
     return SML_OK;
 }

@@ -68,6 +68,8 @@ template <int R>
 __global__ void __launch_bounds__(CONV_THREADS)
 k_conv_fwd(ConvParams P, float *__restrict__ A, uint8_t *__restrict__ Apk, float *__restrict__ rowsq) {
     __shared__ ConvW sw;
+    sml_pdl_wait();
+    sml_pdl_trigger();
     const int gi = blockIdx.y;
     const SmlRowGroup g = P.g[gi];
     load_convw<R>(sw, g.theta);
@@ -118,6 +120,8 @@ template <int R, int MODE, bool THETA>
 __global__ void __launch_bounds__(CONV_THREADS)
 k_conv_bwd(ConvBwdParams P, const float *__restrict__ dA, float l2, float *__restrict__ d_rows) {
     __shared__ ConvW sw;
+    sml_pdl_wait();
+    sml_pdl_trigger();
     __shared__ float s_acc[96];
     const int gi = blockIdx.y;
     const SmlConvBwdGroup bg = P.g[gi];
@@ -242,6 +246,8 @@ k_loss(const float *__restrict__ Y, const float *__restrict__ rowsq, int64_t B, 
        float *__restrict__ gb_user, float *__restrict__ gb_item) {
     __shared__ float s_part[LOSS_WARPS][3];
     __shared__ float s_gb[2][SML_D];
+    sml_pdl_wait();
+    sml_pdl_trigger();
     float gbu[2] = {0.f, 0.f}, gbi[2] = {0.f, 0.f};          // fc2 bias gradients: column sums of dY (this thread's 2 columns)
     if (gb_user && threadIdx.x < 2 * SML_D) s_gb[threadIdx.x / SML_D][threadIdx.x % SML_D] = 0.f;
     __shared__ bool s_last;
@@ -358,8 +364,8 @@ int sml_launch_conv_fwd(const SmlRowGroup *groups, int n_groups, int variant, fl
     for (int i = 0; i < n_groups; ++i) { P.g[i] = groups[i]; if (groups[i].n > max_n) max_n = groups[i].n; }
     if (max_n == 0) return SML_OK;
     dim3 grid(grid_for_rows(max_n), n_groups);
-    if (variant == SML_VARIANT_COM) k_conv_fwd<3><<<grid, CONV_THREADS, 0, st>>>(P, A, Apk, rowsq);
-    else k_conv_fwd<2><<<grid, CONV_THREADS, 0, st>>>(P, A, Apk, rowsq);
+    if (variant == SML_VARIANT_COM) SML_CUDA_OK(sml_launch(k_conv_fwd<3>, grid, dim3(CONV_THREADS), 0, st, P, A, Apk, rowsq));
+    else SML_CUDA_OK(sml_launch(k_conv_fwd<2>, grid, dim3(CONV_THREADS), 0, st, P, A, Apk, rowsq));
     SML_LAUNCH_OK();
     return SML_OK;
 }
@@ -383,7 +389,7 @@ int sml_launch_conv_bwd(const SmlConvBwdGroup *groups, int n_groups, int variant
     // each CTA ends with 95 global atomics onto the same 95 parameters: a few dozen CTAs per group keep that cheap
     if (theta) { const int cap = 32; if (gx > cap) gx = cap; }
     dim3 grid(gx, n_groups);
-#define SML_CB(R_, MODE_, TH_) k_conv_bwd<R_, MODE_, TH_><<<grid, CONV_THREADS, 0, st>>>(P, dA, l2, d_rows)
+#define SML_CB(R_, MODE_, TH_) SML_CUDA_OK(sml_launch(k_conv_bwd<R_, MODE_, TH_>, grid, dim3(CONV_THREADS), 0, st, P, dA, l2, d_rows))
     const bool com = variant == SML_VARIANT_COM;
     if (scatter) {
         if (theta) { if (com) SML_CB(3, 0, true); else SML_CB(2, 0, true); }
@@ -402,8 +408,8 @@ int sml_launch_loss(const float *Y, const float *rowsq, int64_t B, int64_t row_p
                     unsigned int *ticket, cudaStream_t st, float *gb_user, float *gb_item) {
     int64_t blocks = (B + LOSS_WARPS - 1) / LOSS_WARPS;
     if (blocks > 1024) blocks = 1024;   // partials[] holds 3 * 1024 floats
-    k_loss<<<(int)blocks, LOSS_THREADS, 0, st>>>(Y, rowsq, B, row_pos, row_neg, loss_kind, normalize_user, l2, dY, dYpk, scores,
-                                                 loss_out, partials, ticket, gb_user, gb_item);
+    SML_CUDA_OK(sml_launch(k_loss, dim3((unsigned)blocks), dim3(LOSS_THREADS), 0, st, Y, rowsq, B, row_pos, row_neg, loss_kind, normalize_user,
+                           l2, dY, dYpk, scores, loss_out, partials, ticket, gb_user, gb_item));
     SML_LAUNCH_OK();
     return SML_OK;
 }

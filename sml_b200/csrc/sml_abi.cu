@@ -26,6 +26,15 @@ int sml_use_tensor_cores() {
     return v;
 }
 
+int sml_use_pdl() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SML_PDL");
+        v = (e && strcmp(e, "0") == 0) ? 0 : 1;
+    }
+    return v;
+}
+
 static int g_dev_ok[64];     // per-device cache: 1 = verified sm_100-class
 static int g_sm_count[64];
 

@@ -67,6 +67,27 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 static inline size_t sml_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// A step is a chain of ~10 short dependent kernels; with PDL the next kernel's CTAs are scheduled while the previous
+// kernel is still running and do their private prologue (barrier init, TMEM allocation, parameter loads) before
+// blocking in griddepcontrol.wait until the previous grid has completed and flushed.  Every kernel of the chain calls
+// sml_pdl_wait() before it touches global data and sml_pdl_trigger() as early as possible.  SML_PDL=0 disables it.
+int sml_use_pdl();
+#ifdef __CUDACC__
+__device__ __forceinline__ void sml_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void sml_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t sml_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = sml_use_pdl() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+#endif
+
 // ---- internal launchers (defined across the .cu files) ----------------------------------
 
 // One group of rows that share a net and a pair of source tables.

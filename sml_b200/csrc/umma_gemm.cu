@@ -223,6 +223,8 @@ k_umma_gemm(UmmaParams P) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
+    sml_pdl_trigger();
+    sml_pdl_wait();
 
     // instruction descriptor: D=f32 (bit 4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at 17, M>>4 at 24
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM_BM >> 4) << 24);
@@ -353,7 +355,7 @@ int launch_one(const UmmaParams &P, dim3 grid, cudaStream_t st) {
         SML_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<BN>::TOTAL));
         attr_set = true;
     }
-    kern<<<grid, UM_CTA_THREADS, Smem<BN>::TOTAL, st>>>(P);
+    SML_CUDA_OK(sml_launch(kern, grid, dim3(UM_CTA_THREADS), Smem<BN>::TOTAL, st, P));
     SML_LAUNCH_OK();
     return SML_OK;
 }

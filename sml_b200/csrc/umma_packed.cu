@@ -125,6 +125,8 @@ k_umma_packed(PkParams P) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
     const int KC = p.KC;
+    sml_pdl_trigger();      // let the next kernel of the chain start its own prologue
+    sml_pdl_wait();         // barriers and TMEM are set up; only now wait for the producer of our operands
 
     if (warp == 0) {
         if (lane == 0) {
@@ -260,6 +262,8 @@ k_umma_packed(PkParams P) {
 // P2 = W2 as B[64][512] (64-row), P3 = W2^T as B[512][64] (128-row), P4 = W1^T as B[320][512] (64-row).
 __global__ void __launch_bounds__(256) k_pack_theta(const float *__restrict__ theta, uint8_t *__restrict__ out, int n_nets,
                                                     int64_t *adam_state, double lr) {
+    sml_pdl_wait();
+    sml_pdl_trigger();
     if (adam_state && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
         // the step's Adam tick (sml_adam_tick) rides along: step counter + step_size + sqrt(bias_correction2)
         const int64_t t = adam_state[0] + 1;
@@ -309,7 +313,7 @@ int launch_pk(const PkParams &P, dim3 grid, cudaStream_t st) {
         SML_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PkSmem<BN>::TOTAL));
         attr_set = true;
     }
-    kern<<<grid, PKG_THREADS, PkSmem<BN>::TOTAL, st>>>(P);
+    SML_CUDA_OK(sml_launch(kern, grid, dim3(PKG_THREADS), PkSmem<BN>::TOTAL, st, P));
     SML_LAUNCH_OK();
     return SML_OK;
 }
@@ -342,7 +346,7 @@ int sml_launch_umma_packed(const SmlPkProb *probs, int n_probs, int epi, cudaStr
 
 int sml_launch_pack_theta(const float *theta, uint8_t *out, int n_nets, cudaStream_t st, int64_t *adam_state, double lr) {
     dim3 grid(40, 4 * n_nets);
-    k_pack_theta<<<grid, 256, 0, st>>>(theta, out, n_nets, adam_state, lr);
+    SML_CUDA_OK(sml_launch(k_pack_theta, grid, dim3(256), 0, st, theta, out, n_nets, adam_state, lr));
     SML_LAUNCH_OK();
     return SML_OK;
 }

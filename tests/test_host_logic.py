@@ -175,3 +175,46 @@ def test_cli_flags_match_reference():
             assert got[k] == v, (mod.__name__, k, got[k], v)
     a = main_yelp.get_parse().parse_args(["--MF_epochs=3", "--TR_stop_", "yes"])
     assert a.MF_epochs == 3 and a.TR_stop_ is True
+
+
+def test_load_pre_model_accepts_reference_pickle(tmp_path):
+    """The reference pickles a whole ``model.MF.MFbasemode`` (model/transfer.py:322-325).  A file pickled under that module
+    path must load into this package's class even though ``model.MF`` does not exist here."""
+    import sys
+    import types
+    from sml_b200.model import MF as ours
+    from sml_b200.model.transfer import load_pre_model
+    # pickle under the reference's module path
+    pkg = types.ModuleType("model"); sub = types.ModuleType("model.MF")
+    Fake = type("MFbasemode", (ours.MFbasemode,), {"__module__": "model.MF"})
+    sub.MFbasemode = Fake; pkg.MF = sub
+    sys.modules["model"] = pkg; sys.modules["model.MF"] = sub
+    try:
+        torch.manual_seed(1)
+        m = Fake(7, 9, 64)
+        path = str(tmp_path / "pre.pkl")
+        torch.save(m, path)
+    finally:
+        del sys.modules["model"], sys.modules["model.MF"]
+    got = load_pre_model(path, 7, 9, 64, "cpu")
+    assert type(got) is ours.MFbasemode
+    assert torch.equal(got.user_laten.weight, m.user_laten.weight) and got.item_num == 9
+    # a plain state_dict works too and does not disturb the global generator
+    torch.save(got.state_dict(), str(tmp_path / "sd.pt"))
+    torch.manual_seed(5); a = torch.rand(1)
+    torch.manual_seed(5); got2 = load_pre_model(str(tmp_path / "sd.pt"), 7, 9, 64, "cpu"); b = torch.rand(1)
+    assert torch.equal(a, b) and torch.equal(got2.item_laten.weight, m.item_laten.weight)
+
+
+def test_memory_stream_branches():
+    from sml_b200.data.memory_stream import MemoryStream
+    periods = [(np.zeros((3, 2), np.int64) + p, np.zeros((3, 5), np.int64) + p) for p in range(6)]
+    ds = MemoryStream(periods, 10, 20, online_train_time=1, online_test_time=4)
+    set_t, set_tt, now_test, val = ds.next_train(0)            # now = 1: train-only branch
+    assert now_test is None and set_t[0, 0] == 1 and set_tt[0, 0] == 2 and val[0, 0] == 2 and set_tt.shape[1] == 2
+    set_t, set_tt, now_test, val = ds.next_train(2)            # now = 3, next = 4 = first test period
+    assert now_test[0, 0] == 4 and val[0, 0] == 4 and set_t[0, 0] == 3
+    assert ds.next_train(4) == (None, None, None, None)
+    ds.reinit(); assert ds.test_count == 0
+    stop = MemoryStream(periods, 10, 20, online_train_time=1, online_test_time=4, tr_stop=True)
+    assert stop.next_train(2)[1] is None
