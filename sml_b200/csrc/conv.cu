@@ -77,7 +77,10 @@ k_conv_fwd(ConvParams P, float *__restrict__ A, uint8_t *__restrict__ Apk, float
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * CONV_WARPS + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * CONV_WARPS;
-    for (int64_t r = warp0; r < g.n; r += nwarps) {
+    // two warps per row: warp 2r+h converts latent dims [32h, 32h+32) (both load the whole row for the norm)
+    for (int64_t wr = warp0; wr < 2 * g.n; wr += nwarps) {
+        const int64_t r = wr >> 1;
+        const int h0 = (int)(wr & 1);
         const int64_t id = g.ids ? __ldg(g.ids + r) : r;
         const float *xt = g.x_t + id * g.pitch;
         const float *xh = g.x_hat + id * g.pitch;
@@ -91,13 +94,15 @@ k_conv_fwd(ConvParams P, float *__restrict__ A, uint8_t *__restrict__ Apk, float
         }
         if (rowsq) {
             const float q = warp_sum(x1[0] * x1[0] + x1[1] * x1[1]);
-            if (lane == 0) rowsq[g.row0 + r] = q;
+            if (lane == 0 && h0 == 0) rowsq[g.row0 + r] = q;
         }
         float *a = A ? A + (g.row0 + r) * SML_FC1_IN : nullptr;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        {
+            const int h = h0;
+            const float x0h = h0 ? x0[1] : x0[0], x1h = h0 ? x1[1] : x1[0], x2h = h0 ? x2[1] : x2[0];   // no dynamic register indexing
             float z1[10], h1[10], z2[5];
-            conv_point<R>(sw, x0[h], x1[h], x2[h], z1, h1, z2);
+            conv_point<R>(sw, x0h, x1h, x2h, z1, h1, z2);
 #pragma unroll
             for (int m = 0; m < 5; ++m) {
                 const float v = sml_gelu(z2[m]);
@@ -148,7 +153,10 @@ k_conv_bwd(ConvBwdParams P, const float *__restrict__ dA, float l2, float *__res
             for (int r = 0; r < 3; ++r) gw1[c][r] = 0.f;
         }
     }
-    for (int64_t r = warp0; r < g.n; r += nwarps) {
+    // two warps per row: warp 2r+h converts latent dims [32h, 32h+32) (both load the whole row for the norm)
+    for (int64_t wr = warp0; wr < 2 * g.n; wr += nwarps) {
+        const int64_t r = wr >> 1;
+        const int h0 = (int)(wr & 1);
         const int64_t id = g.ids ? __ldg(g.ids + r) : r;
         const float *xt = g.x_t + id * g.pitch;
         const float *xh = g.x_hat + id * g.pitch;
@@ -162,9 +170,11 @@ k_conv_bwd(ConvBwdParams P, const float *__restrict__ dA, float l2, float *__res
         }
         const float *da = dA + (g.row0 + r) * SML_FC1_IN;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        {
+            const int h = h0;
+            const float x0h = h0 ? x0[1] : x0[0], x1h = h0 ? x1[1] : x1[0], x2h = h0 ? x2[1] : x2[0];   // no dynamic register indexing
             float z1[10], h1[10], z2[5];
-            conv_point<R>(sw, x0[h], x1[h], x2[h], z1, h1, z2);
+            conv_point<R>(sw, x0h, x1h, x2h, z1, h1, z2);
             float dz2[5];
 #pragma unroll
             for (int m = 0; m < 5; ++m) dz2[m] = __ldg(da + m * SML_D + lane + 32 * h) * sml_gelu_grad(z2[m]);
@@ -178,9 +188,9 @@ k_conv_bwd(ConvBwdParams P, const float *__restrict__ dA, float l2, float *__res
                 dx1 = fmaf(sw.w1[c][1], dz1, dx1);
                 if (THETA) {
                     gb1[c] += dz1;
-                    gw1[c][0] = fmaf(dz1, x0[h], gw1[c][0]);
-                    gw1[c][1] = fmaf(dz1, x1[h], gw1[c][1]);
-                    if (R == 3) gw1[c][2] = fmaf(dz1, x2[h], gw1[c][2]);
+                    gw1[c][0] = fmaf(dz1, x0h, gw1[c][0]);
+                    gw1[c][1] = fmaf(dz1, x1h, gw1[c][1]);
+                    if (R == 3) gw1[c][2] = fmaf(dz1, x2h, gw1[c][2]);
                 }
             }
             if (THETA) {
@@ -193,7 +203,7 @@ k_conv_bwd(ConvBwdParams P, const float *__restrict__ dA, float l2, float *__res
             }
             if (MODE == 0) {
                 // dense-gradient scatter: grad of l2*0.5*sum(w^2) is l2*w per occurrence (transfer.py:486)
-                atomicAdd(bg.g_tab + id * SML_D + lane + 32 * h, fmaf(l2, x1[h], dx1));
+                atomicAdd(bg.g_tab + id * SML_D + lane + 32 * h, fmaf(l2, x1h, dx1));
             } else if (d_rows) {
                 d_rows[(g.row0 + r) * SML_D + lane + 32 * h] = dx1;
             }
@@ -346,7 +356,7 @@ __global__ void __launch_bounds__(256) k_row_normalize(float *__restrict__ Y, in
 }
 
 int grid_for_rows(int64_t max_n) {
-    int64_t blocks = (max_n + CONV_WARPS - 1) / CONV_WARPS;
+    int64_t blocks = (2 * max_n + CONV_WARPS - 1) / CONV_WARPS;      // two warps per row
     const int64_t cap = (int64_t)sml_sm_count() * 16;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
