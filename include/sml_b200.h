@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SML_ABI_VERSION 1
+#define SML_ABI_VERSION 2
 
 #define SML_OK 0
 #define SML_E_BADARG (-1)
@@ -118,8 +118,12 @@ int sml_transfer_fwd(const float *x_t, const float *x_hat, const int64_t *ids, i
  * torch.optim.Adam keeps one step counter per parameter and derives step_size and
  * sqrt(bias_correction2) from it on the host (model/transfer.py:392-393).  To stay
  * graph-capturable the counter lives on the device: sml_adam_tick increments
- * state[0] (int64) and writes step_size = lr/(1-b1^t) and sqrt(1-b2^t) as floats at
- * state[1], state[2] (computed in double). `state` = 4 int64 slots. */
+ * state[0] (int64) and writes step_size = lr/(1-b1^t) and sqrt(1-b2^t) (computed in
+ * double) as two floats into the int64 slot state[1].  `state` = 4 int64 slots; if
+ * state[2] != 0 the buffer continues with SML_ADAM_HISTORY more slots and the tick also
+ * records the float pair of step t at slot 4 + (t mod SML_ADAM_HISTORY), which is what
+ * the row-lazy update below replays. */
+#define SML_ADAM_HISTORY 4096
 int sml_adam_tick(int64_t *state, double lr, double beta1, double beta2, void *stream);
 /* Dense Adam over n floats (torch defaults eps=1e-8, amsgrad off; coupled L2 weight_decay):
  *   g' = g + wd*p; m += (g'-m)*(1-b1); v = b2*v + (1-b2)*g'^2; p -= step_size*m/(sqrt(v)/sqrt(bc2)+eps)
@@ -127,6 +131,22 @@ int sml_adam_tick(int64_t *state, double lr, double beta1, double beta2, void *s
  * model/transfer.py:464-465,702). */
 int sml_adam_dense(float *p, float *m, float *v, float *g, int64_t n, const int64_t *state, double beta1, double beta2,
                    double eps, double weight_decay, int zero_grad, void *stream);
+
+/* Row-lazy, bit-identical form of the dense update for embedding tables ([n_rows, 64], weight_decay 0).
+ * The reference's MF optimizer is DENSE Adam over whole nn.Embedding tables (model/MF.py:21-24,
+ * model/transfer.py:392): a row without gradient still moves through its momentum tail every step.
+ * Instead of sweeping the tables every step, each row carries the number of the last step applied to
+ * it (stamp[row], int32) and the zero-gradient steps it missed are replayed in registers -- same
+ * operations in the same order as sml_adam_dense, so the tables are bit-identical to the dense sweep --
+ *   sml_adam_rows(apply = 0): bring the listed rows up to step t-1, before a step reads them;
+ *   sml_adam_rows(apply = 1): apply step t with the accumulated gradient rows g[id], re-zero them;
+ *   sml_adam_flush:           bring EVERY row up to step t (before the table is read as a whole).
+ * t = state[0]; state must carry the history (state[2] != 0) and no row may lag more than
+ * SML_ADAM_HISTORY - 1 steps.  Duplicate ids are fine (first claimant updates the row). */
+int sml_adam_rows(float *p, float *m, float *v, float *g, int32_t *stamp, const int64_t *ids, int64_t n_ids, int64_t n_rows,
+                  const int64_t *state, int apply, double beta1, double beta2, double eps, void *stream);
+int sml_adam_flush(float *p, float *m, float *v, int32_t *stamp, int64_t n_rows, const int64_t *state, double beta1,
+                   double beta2, double eps, void *stream);
 
 /* ---- SML steps ----------------------------------------------------------------------
  * Shared argument block for the two hot loops.  Rows [0,B) of every workspace matrix are
@@ -160,6 +180,10 @@ typedef struct {
     /* floats between consecutive rows of last_* / hat_* (0 = 64).  sml_run_mf_grads only: lets the four
      * "tables" be views into exchanged [last | hat] row pairs (pitch 128) without a de-interleave copy. */
     int64_t table_pitch;
+    /* MF step only, optional: per-row "last Adam step applied" stamps ([n_users] / [n_items] int32).  Non-null
+     * selects the row-lazy exact Adam (sml_adam_rows) instead of the dense sweeps: sml_mf_epoch flushes both
+     * tables before it returns, after sml_mf_step the caller must (sml_adam_flush) before reading the tables. */
+    int32_t *stamp_user, *stamp_item;
 } sml_step_args;
 
 size_t sml_step_workspace_bytes(int64_t batch);

@@ -286,6 +286,23 @@ def gen_period_run(ns, stop=False, news=False):
     ns.transfer.SampleDaset = ns.dataset.offlineDataset_withsample
 
 
+def gen_select_neg(ns):
+    """Reference test-file builder (data/dataset2.py:356-414) on a small stream, numpy seed 77, neg_num 25."""
+    rng = np.random.default_rng(3)
+    files = [np.stack([rng.integers(0, 40, 90), rng.integers(0, 1500, 90)], 1).astype(np.int64) for _ in range(5)]
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "mini", "test"))
+        np.save(os.path.join(tmp, "mini", "information.npy"), np.array([450, 40, 1500]))
+        for k, f in enumerate(files):
+            np.save(os.path.join(tmp, "mini", "%d.npy" % k), f)
+        np.random.seed(77)
+        ns.dataset2.select_neg_forinteraction(path=tmp + "/", datasetname="mini", file_path_list=[str(k) for k in range(5)],
+                                              leave_for_init_train=0.6, neg_num=25)
+        tests = {"test%d" % k: np.load(os.path.join(tmp, "mini", "test", "%d.npy" % k)) for k in (3, 4)}
+    npz("select_neg.npz", seed=np.array(77), neg_num=np.array(25), leave=np.array(0.6),
+        **{"file%d" % k: f for k, f in enumerate(files)}, **tests)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
@@ -294,7 +311,7 @@ def main():
     ns = ref_harness.load()
     gens = dict(transfer_fwd=gen_transfer_fwd, run_mf=gen_run_mf, mf_steps=gen_mf_steps, tr_steps=gen_tr_steps,
                 eval=gen_eval, period_run=gen_period_run, period_run_stop=lambda n: gen_period_run(n, stop=True),
-                period_run_news=lambda n: gen_period_run(n, news=True))
+                period_run_news=lambda n: gen_period_run(n, news=True), select_neg=gen_select_neg)
     for name, fn in gens.items():
         if a.only and name not in a.only.split(","):
             continue

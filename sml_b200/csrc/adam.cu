@@ -3,9 +3,13 @@
 //
 // The MF optimizer in the reference is DENSE Adam over whole nn.Embedding tables
 // (nn.Embedding(sparse=False), model/MF.py:21-24): rows touched at an earlier step keep moving
-// through the momentum tail, so a lazy/sparse Adam is not equivalent.  The dense sweep is
-// HBM-bound: per element read p, m, v, g and write p, m, v (+ the zeroed g that replaces
-// zero_grad()): 32 B per float, all 128-bit accesses, grid sized to the SM count.
+// through the momentum tail, so the usual lazy/sparse Adam is not equivalent.  Two exact forms:
+//  * k_adam_dense: the sweep.  HBM-bound: per element read p, m, v, g and write p, m, v (+ the zeroed g
+//    that replaces zero_grad()): 32 B per float, all 128-bit accesses, grid sized to the SM count.
+//  * k_adam_rows / k_adam_flush: the same arithmetic, row-lazy.  A row that had no gradient for k steps
+//    is brought up to date by replaying those k zero-gradient steps in registers (the per-step scalars come
+//    from the history ring the tick kernel keeps), so only the 3B rows of a batch move per step and the
+//    whole table moves once per flush: same bits as the sweep, 1/steps of its HBM traffic.
 #include <math.h>
 
 #include "sml_common.cuh"
@@ -15,24 +19,7 @@ namespace {
 __global__ void k_adam_tick(int64_t *state, double lr, double beta1, double beta2) {
     sml_pdl_wait();
     sml_pdl_trigger();
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        const int64_t t = state[0] + 1;
-        state[0] = t;
-        const double bc1 = 1.0 - pow(beta1, (double)t);
-        const double bc2 = 1.0 - pow(beta2, (double)t);
-        float *f = reinterpret_cast<float *>(state + 1);
-        f[0] = (float)(lr / bc1);          // step_size
-        f[1] = (float)sqrt(bc2);           // bias_correction2_sqrt
-    }
-}
-
-__device__ __forceinline__ void adam1(float &p, float &m, float &v, float g, float b1c, float beta2, float b2c,
-                                      float step_size, float bc2_sqrt, float eps, float wd) {
-    if (wd != 0.f) g = fmaf(wd, p, g);                 // grad.add(param, alpha=weight_decay)
-    m = fmaf(g - m, b1c, m);                           // exp_avg.lerp_(grad, 1 - beta1)
-    v = fmaf(b2c * g, g, beta2 * v);                   // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
-    const float denom = sqrtf(v) / bc2_sqrt + eps;
-    p = p - step_size * (m / denom);                   // param.addcdiv_(exp_avg, denom, value=-step_size)
+    if (threadIdx.x == 0 && blockIdx.x == 0) sml_adam_tick_body(state, lr, beta1, beta2);
 }
 
 template <bool ZERO>
@@ -48,16 +35,123 @@ k_adam_dense(float4 *__restrict__ p, float4 *__restrict__ m, float4 *__restrict_
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 pp = p[i], mm = m[i], vv = v[i];
         const float4 gg = g[i];
-        adam1(pp.x, mm.x, vv.x, gg.x, b1c, beta2, b2c, step_size, bc2_sqrt, eps, wd);
-        adam1(pp.y, mm.y, vv.y, gg.y, b1c, beta2, b2c, step_size, bc2_sqrt, eps, wd);
-        adam1(pp.z, mm.z, vv.z, gg.z, b1c, beta2, b2c, step_size, bc2_sqrt, eps, wd);
-        adam1(pp.w, mm.w, vv.w, gg.w, b1c, beta2, b2c, step_size, bc2_sqrt, eps, wd);
+        sml_adam1(pp.x, mm.x, vv.x, gg.x, b1c, beta2, b2c, step_size, bc2_sqrt, eps, wd);
+        sml_adam1(pp.y, mm.y, vv.y, gg.y, b1c, beta2, b2c, step_size, bc2_sqrt, eps, wd);
+        sml_adam1(pp.z, mm.z, vv.z, gg.z, b1c, beta2, b2c, step_size, bc2_sqrt, eps, wd);
+        sml_adam1(pp.w, mm.w, vv.w, gg.w, b1c, beta2, b2c, step_size, bc2_sqrt, eps, wd);
         p[i] = pp; m[i] = mm; v[i] = vv;
         if (ZERO) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
+// ---- row-lazy exact Adam ---------------------------------------------------------------------
+struct AdamRowsGroup {
+    float *p, *m, *v, *g;
+    int32_t *stamp;
+    const int64_t *ids;
+    int64_t n;
+};
+struct AdamRowsParams { AdamRowsGroup g[3]; };
+
+__device__ __forceinline__ float2 adam_hist(const int64_t *state, int s) {
+    return *reinterpret_cast<const float2 *>(state + 4 + (s & (SML_ADAM_HISTORY - 1)));
+}
+
+// One warp per listed id (2 floats per lane).  The claim on stamp[id] makes exactly one warp the owner of a row that
+// appears several times in the batch.
+template <bool APPLY>
+__global__ void __launch_bounds__(256)
+k_adam_rows(AdamRowsParams P, const int64_t *__restrict__ state, float b1c, float beta2, float b2c, float eps) {
+    sml_pdl_wait();
+    sml_pdl_trigger();
+    const int t = (int)state[0];
+    const int target = APPLY ? t : t - 1;
+    const int lane = threadIdx.x & 31;
+    const int64_t n0 = P.g[0].n, n1 = n0 + P.g[1].n, total = n1 + P.g[2].n;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += warps) {
+        const int gi = w < n0 ? 0 : (w < n1 ? 1 : 2);
+        const AdamRowsGroup &G = P.g[gi];
+        const int64_t id = G.ids[w - (gi == 0 ? 0 : (gi == 1 ? n0 : n1))];
+        int old = 0;
+        if (lane == 0) old = atomicExch(G.stamp + id, target);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old >= target) continue;
+        const size_t e = (size_t)id * SML_D + 2 * lane;
+        float2 pp = *reinterpret_cast<float2 *>(G.p + e), mm = *reinterpret_cast<float2 *>(G.m + e),
+               vv = *reinterpret_cast<float2 *>(G.v + e);
+        // exp_avg = exp_avg_sq = +0 (a row no gradient ever reached): a zero-gradient step changes nothing, bit for bit
+        const bool idle = (__float_as_uint(mm.x) | __float_as_uint(mm.y) | __float_as_uint(vv.x) | __float_as_uint(vv.y)) == 0u;
+        for (int s = idle ? t : old + 1; s < t; ++s) {   // the zero-gradient steps this row missed
+            const float2 c = adam_hist(state, s);
+            sml_adam1(pp.x, mm.x, vv.x, 0.f, b1c, beta2, b2c, c.x, c.y, eps, 0.f);
+            sml_adam1(pp.y, mm.y, vv.y, 0.f, b1c, beta2, b2c, c.x, c.y, eps, 0.f);
+        }
+        if (APPLY) {
+            const float2 c = adam_hist(state, t);
+            const float2 gg = *reinterpret_cast<float2 *>(G.g + e);
+            sml_adam1(pp.x, mm.x, vv.x, gg.x, b1c, beta2, b2c, c.x, c.y, eps, 0.f);
+            sml_adam1(pp.y, mm.y, vv.y, gg.y, b1c, beta2, b2c, c.x, c.y, eps, 0.f);
+            *reinterpret_cast<float2 *>(G.g + e) = make_float2(0.f, 0.f);
+        }
+        *reinterpret_cast<float2 *>(G.p + e) = pp;
+        *reinterpret_cast<float2 *>(G.m + e) = mm;
+        *reinterpret_cast<float2 *>(G.v + e) = vv;
+    }
+}
+
+// Every row up to step t: 16 threads (one float4 each) per row, the 16 sit in one warp.
+__global__ void __launch_bounds__(256)
+k_adam_flush(float4 *__restrict__ p, float4 *__restrict__ m, float4 *__restrict__ v, int32_t *__restrict__ stamp, int64_t n_rows,
+             const int64_t *__restrict__ state, float b1c, float beta2, float b2c, float eps) {
+    sml_pdl_wait();
+    sml_pdl_trigger();
+    const int t = (int)state[0];
+    const int64_t n4 = n_rows * (SML_D / 4);
+    const int64_t n4_up = (n4 + 31) & ~(int64_t)31;      // whole warps stay in the loop for the __syncwarp
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4_up; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool live = i < n4;
+        const int64_t row = i >> 4;
+        const int old = live ? stamp[row] : t;
+        __syncwarp();
+        if (old < t) {
+            float4 pp = p[i], mm = m[i], vv = v[i];
+            const bool idle = (__float_as_uint(mm.x) | __float_as_uint(mm.y) | __float_as_uint(mm.z) | __float_as_uint(mm.w) |
+                               __float_as_uint(vv.x) | __float_as_uint(vv.y) | __float_as_uint(vv.z) | __float_as_uint(vv.w)) == 0u;
+            for (int s = idle ? t + 1 : old + 1; s <= t; ++s) {
+                const float2 c = adam_hist(state, s);
+                sml_adam1(pp.x, mm.x, vv.x, 0.f, b1c, beta2, b2c, c.x, c.y, eps, 0.f);
+                sml_adam1(pp.y, mm.y, vv.y, 0.f, b1c, beta2, b2c, c.x, c.y, eps, 0.f);
+                sml_adam1(pp.z, mm.z, vv.z, 0.f, b1c, beta2, b2c, c.x, c.y, eps, 0.f);
+                sml_adam1(pp.w, mm.w, vv.w, 0.f, b1c, beta2, b2c, c.x, c.y, eps, 0.f);
+            }
+            if (!idle) { p[i] = pp; m[i] = mm; v[i] = vv; }
+            if ((i & 15) == 0) stamp[row] = t;
+        }
+    }
+}
+
 }  // namespace
+
+int sml_launch_adam_rows(const SmlAdamRows *rows, int n_groups, const int64_t *state, int apply, double beta1, double beta2,
+                         double eps, cudaStream_t st) {
+    SML_REQUIRE(n_groups >= 1 && n_groups <= 3, SML_E_BADARG, "adam_rows: bad group count %d", n_groups);
+    AdamRowsParams P = {};
+    int64_t total = 0;
+    for (int i = 0; i < n_groups; ++i) {
+        P.g[i] = AdamRowsGroup{rows[i].p, rows[i].m, rows[i].v, rows[i].g, rows[i].stamp, rows[i].ids, rows[i].n};
+        total += rows[i].n;
+    }
+    if (total == 0) return SML_OK;
+    int64_t blocks = (total + 7) / 8;                       // 8 warps per CTA, one warp per id
+    const int64_t cap = (int64_t)sml_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    const float b1c = (float)(1.0 - beta1), b2 = (float)beta2, b2c = (float)(1.0 - beta2), e = (float)eps;
+    if (apply) SML_CUDA_OK(sml_launch(k_adam_rows<true>, dim3((unsigned)blocks), dim3(256), 0, st, P, state, b1c, b2, b2c, e));
+    else SML_CUDA_OK(sml_launch(k_adam_rows<false>, dim3((unsigned)blocks), dim3(256), 0, st, P, state, b1c, b2, b2c, e));
+    SML_LAUNCH_OK();
+    return SML_OK;
+}
 
 extern "C" {
 
@@ -89,6 +183,36 @@ int sml_adam_dense(float *p, float *m, float *v, float *g, int64_t n, const int6
     else
         SML_CUDA_OK(sml_launch(k_adam_dense<false>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (float4 *)p, (float4 *)m, (float4 *)v, (float4 *)g, n4,
                                state, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps, (float)weight_decay));
+    SML_LAUNCH_OK();
+    return SML_OK;
+}
+
+
+int sml_adam_rows(float *p, float *m, float *v, float *g, int32_t *stamp, const int64_t *ids, int64_t n_ids, int64_t n_rows,
+                  const int64_t *state, int apply, double beta1, double beta2, double eps, void *stream) {
+    int rc = sml_check_device();
+    if (rc) return rc;
+    SML_REQUIRE(n_ids >= 0 && n_rows >= 0, SML_E_BADARG, "sml_adam_rows: negative size");
+    if (n_ids == 0) return SML_OK;
+    SML_REQUIRE(p && m && v && stamp && ids && state && (g || !apply), SML_E_BADARG, "sml_adam_rows: null pointer");
+    SmlAdamRows r = {p, m, v, g, stamp, ids, n_ids};
+    return sml_launch_adam_rows(&r, 1, state, apply, beta1, beta2, eps, (cudaStream_t)stream);
+}
+
+int sml_adam_flush(float *p, float *m, float *v, int32_t *stamp, int64_t n_rows, const int64_t *state, double beta1,
+                   double beta2, double eps, void *stream) {
+    int rc = sml_check_device();
+    if (rc) return rc;
+    SML_REQUIRE(n_rows >= 0, SML_E_BADARG, "sml_adam_flush: negative n_rows");
+    if (n_rows == 0) return SML_OK;
+    SML_REQUIRE(p && m && v && stamp && state, SML_E_BADARG, "sml_adam_flush: null pointer");
+    SML_REQUIRE((((uintptr_t)p | (uintptr_t)m | (uintptr_t)v) & 15) == 0, SML_E_BADARG, "sml_adam_flush: pointers must be 16-byte aligned");
+    const int64_t n4 = n_rows * (SML_D / 4);
+    int64_t blocks = (n4 + 255) / 256;
+    const int64_t cap = (int64_t)sml_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    SML_CUDA_OK(sml_launch(k_adam_flush, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (float4 *)p, (float4 *)m, (float4 *)v, stamp,
+                           n_rows, state, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps));
     SML_LAUNCH_OK();
     return SML_OK;
 }

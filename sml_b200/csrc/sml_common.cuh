@@ -88,7 +88,47 @@ inline cudaError_t sml_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 }
 #endif
 
+// ---- Adam scalars (torch.optim.Adam, model/transfer.py:392-393) ------------------------------
+// One tick: t += 1, step_size = lr / (1 - b1^t) and sqrt(1 - b2^t) in double, rounded to float; recorded in the
+// history ring when the state carries one (see sml_adam_tick in the header).
+#ifdef __CUDACC__
+__device__ __forceinline__ void sml_adam_tick_body(int64_t *state, double lr, double beta1, double beta2) {
+    const int64_t t = state[0] + 1;
+    state[0] = t;
+    const float ss = (float)(lr / (1.0 - pow(beta1, (double)t)));
+    const float bs = (float)sqrt(1.0 - pow(beta2, (double)t));
+    float *f = reinterpret_cast<float *>(state + 1);
+    f[0] = ss;
+    f[1] = bs;
+    if (state[2] != 0) {
+        float *h = reinterpret_cast<float *>(state + 4 + (t & (SML_ADAM_HISTORY - 1)));
+        h[0] = ss;
+        h[1] = bs;
+    }
+}
+
+// One element of one Adam step; shared by the dense sweep and the row-lazy replay so both round identically.
+__device__ __forceinline__ void sml_adam1(float &p, float &m, float &v, float g, float b1c, float beta2, float b2c,
+                                          float step_size, float bc2_sqrt, float eps, float wd) {
+    if (wd != 0.f) g = fmaf(wd, p, g);                 // grad.add(param, alpha=weight_decay)
+    m = fmaf(g - m, b1c, m);                           // exp_avg.lerp_(grad, 1 - beta1)
+    v = fmaf(b2c * g, g, beta2 * v);                   // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+    const float denom = sqrtf(v) / bc2_sqrt + eps;
+    p = p - step_size * (m / denom);                   // param.addcdiv_(exp_avg, denom, value=-step_size)
+}
+#endif
+
 // ---- internal launchers (defined across the .cu files) ----------------------------------
+
+// Row-lazy Adam over up to three id lists (user ids -> user table, positive / negative item ids -> item table).
+struct SmlAdamRows {
+    float *p, *m, *v, *g;
+    int32_t *stamp;
+    const int64_t *ids;
+    int64_t n;
+};
+int sml_launch_adam_rows(const SmlAdamRows *rows, int n_groups, const int64_t *state, int apply, double beta1, double beta2,
+                         double eps, cudaStream_t st);
 
 // One group of rows that share a net and a pair of source tables.
 struct SmlRowGroup {

@@ -263,6 +263,14 @@ int mf_step_impl(const sml_step_args *a, bool pack_theta, void *stream) {
     const StepWs w = carve(a->workspace, a->batch);
     int rc = sml_adam_tick(a->adam_state, a->lr, 0.9, 0.999, stream);
     if (rc) return rc;
+    const bool lazy = a->stamp_user != nullptr;
+    SmlAdamRows ar[3] = {{a->hat_user, a->m_user, a->v_user, a->g_user, a->stamp_user, a->user, a->batch},
+                         {a->hat_item, a->m_item, a->v_item, a->g_item, a->stamp_item, a->item, a->batch},
+                         {a->hat_item, a->m_item, a->v_item, a->g_item, a->stamp_item, a->neg, a->batch}};
+    if (lazy) {   // row-lazy exact Adam: the rows this batch reads catch up with the zero-gradient steps they missed
+        rc = sml_launch_adam_rows(ar, 3, a->adam_state, 0, 0.9, 0.999, 1e-8, st);
+        if (rc) return rc;
+    }
     rc = forward_and_loss(a, w, true, false, pack_theta, (float)a->l2, nullptr, st);
     if (rc) return rc;
     rc = fc1_dgrad(a, w, st);
@@ -272,10 +280,17 @@ int mf_step_impl(const sml_step_args *a, bool pack_theta, void *stream) {
     SmlConvBwdGroup bg[3] = {{g[0], a->g_user, nullptr}, {g[1], a->g_item, nullptr}, {g[2], a->g_item, nullptr}};
     rc = sml_launch_conv_bwd(bg, 3, a->variant, w.dA, (float)a->l2, nullptr, st);
     if (rc) return rc;
+    if (lazy) return sml_launch_adam_rows(ar, 3, a->adam_state, 1, 0.9, 0.999, 1e-8, st);   // this step, on the touched rows
     // dense Adam on both latent tables, weight_decay = 0 (model/transfer.py:392); also re-zeroes the gradients
     rc = sml_adam_dense(a->hat_user, a->m_user, a->v_user, a->g_user, a->n_users * SML_D, a->adam_state, 0.9, 0.999, 1e-8, 0.0, 1, stream);
     if (rc) return rc;
     return sml_adam_dense(a->hat_item, a->m_item, a->v_item, a->g_item, a->n_items * SML_D, a->adam_state, 0.9, 0.999, 1e-8, 0.0, 1, stream);
+}
+
+int mf_flush(const sml_step_args *a, void *stream) {
+    int rc = sml_adam_flush(a->hat_user, a->m_user, a->v_user, a->stamp_user, a->n_users, a->adam_state, 0.9, 0.999, 1e-8, stream);
+    if (rc) return rc;
+    return sml_adam_flush(a->hat_item, a->m_item, a->v_item, a->stamp_item, a->n_items, a->adam_state, 0.9, 0.999, 1e-8, stream);
 }
 
 int check_mf(const sml_step_args *a) {
@@ -286,6 +301,7 @@ int check_mf(const sml_step_args *a) {
     SML_REQUIRE(a->table_pitch == 0 || a->table_pitch == SML_D, SML_E_BADARG, "sml_mf_step: tables must be dense [rows, 64]");
     SML_REQUIRE(a->g_user && a->g_item && a->m_user && a->v_user && a->m_item && a->v_item && a->adam_state, SML_E_BADARG,
                 "sml_mf_step: null gradient / Adam-state pointer");
+    SML_REQUIRE((a->stamp_user != nullptr) == (a->stamp_item != nullptr), SML_E_BADARG, "sml_mf_step: give both row stamps or neither");
     return SML_OK;
 }
 
@@ -440,6 +456,7 @@ int sml_mf_epoch(const sml_step_args *a, int64_t n_total, void *stream) {
     if (rc) return rc;
     sml_step_args s = *a;
     bool first = true;
+    int since_flush = 0;
     for (int64_t off = 0; off < n_total; off += a->batch) {
         s.user = a->user + off; s.item = a->item + off; s.neg = a->neg + off;
         s.batch = (n_total - off) < a->batch ? (n_total - off) : a->batch;
@@ -448,6 +465,12 @@ int sml_mf_epoch(const sml_step_args *a, int64_t n_total, void *stream) {
         rc = mf_step_impl(&s, first || s.batch != a->batch, stream);
         if (rc) return rc;
         first = false;
+        if (a->stamp_user && (++since_flush >= SML_ADAM_HISTORY - 1 || off + a->batch >= n_total)) {
+            // row-lazy Adam: every row up to date before the tables are read as a whole (and before the history ring wraps)
+            rc = mf_flush(a, stream);
+            if (rc) return rc;
+            since_flush = 0;
+        }
     }
     return SML_OK;
 }

@@ -266,11 +266,7 @@ __global__ void __launch_bounds__(256) k_pack_theta(const float *__restrict__ th
     sml_pdl_trigger();
     if (adam_state && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
         // the step's Adam tick (sml_adam_tick) rides along: step counter + step_size + sqrt(bias_correction2)
-        const int64_t t = adam_state[0] + 1;
-        adam_state[0] = t;
-        float *f = reinterpret_cast<float *>(adam_state + 1);
-        f[0] = (float)(lr / (1.0 - pow(0.9, (double)t)));
-        f[1] = (float)sqrt(1.0 - pow(0.999, (double)t));
+        sml_adam_tick_body(adam_state, lr, 0.9, 0.999);
     }
     const int net = blockIdx.y >> 2, which = blockIdx.y & 3;
     if (net >= n_nets) return;

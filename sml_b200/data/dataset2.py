@@ -9,6 +9,7 @@ print statistics (data/dataset2.py:234-237), and ``np.load`` results are cached 
 from __future__ import annotations
 
 import copy
+import os
 
 import numpy as np
 
@@ -143,3 +144,47 @@ class transfer_data(object):
             print("real test:", self.test_list[self.test_count])
             self.test_count += 1
             return set_t, set_tt, now_test, val
+
+
+def select_neg_forinteraction(path="dataset/", datasetname="News", file_path_list=None, leave_for_init_train=0.7, neg_num=999,
+                              extra_draws=1000):
+    """Test-file builder (reference: data/dataset2.py:356-414): for every interaction of the periods after the first
+    ``round(len * leave_for_init_train)``, ``neg_num`` distinct items seen so far that the user has not interacted
+    with (up to and including that row), in random order; writes ``<path>/<name>/test/<i>.npy`` = [user, item, negs...].
+
+    Draws from the global numpy RNG exactly like the reference (one ``np.random.choice`` of neg_num + 1000 per attempt,
+    then one ``np.random.shuffle``), and indexes the same ``list(set)`` ordering of the items seen so far, so the files
+    are bit-identical for the same ``np.random.seed``; the reference rebuilds that item array (O(items)) for every row,
+    here it is rebuilt only when a new item appears.  Returns the list of test arrays."""
+    base = os.path.join(path, datasetname)
+    inter_all = [np.load(os.path.join(base, f + ".npy")) for f in file_path_list]
+    n_files = len(inter_all)
+    start = round(n_files * leave_for_init_train)
+    seen = np.concatenate(inter_all[0:start], axis=0)
+    user_item = {}
+    for u, it in zip(seen[:, 0], seen[:, 1]):
+        user_item.setdefault(u, set()).add(it)
+    items_so_far = set(np.unique(seen[:, 1]))
+    pool = np.array(list(items_so_far))
+    out = []
+    os.makedirs(os.path.join(base, "test"), exist_ok=True)
+    for p in range(start, n_files):
+        inter = inter_all[p]
+        negs = np.empty((inter.shape[0], neg_num), dtype=pool.dtype)
+        for r, (u, it) in enumerate(zip(inter[:, 0], inter[:, 1])):
+            if it not in items_so_far:
+                items_so_far.add(it)
+                pool = np.array(list(items_so_far))          # iteration order of the set = the reference's all_item
+            hist = user_item.setdefault(u, set())
+            hist.add(it)
+            have = np.fromiter(hist, dtype=pool.dtype, count=len(hist))
+            while True:
+                cand = np.setdiff1d(np.random.choice(pool, neg_num + extra_draws), have)   # sorted, unique
+                if cand.shape[0] >= neg_num:
+                    break
+            np.random.shuffle(cand)
+            negs[r] = cand[:neg_num]
+        test = np.concatenate([inter, negs], axis=1)
+        np.save(os.path.join(base, "test", str(p) + ".npy"), test)
+        out.append(test)
+    return out

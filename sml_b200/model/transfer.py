@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import copy
 import io
+import os
 import pickle
 import time
 
@@ -168,7 +169,14 @@ class meta_train(object):
         self.transfer_optimizer = FusedAdam(self.transfer.parameters(), lr=args.TR_lr, weight_decay=args.TR_l2)
         z = torch.zeros_like
         self._mf = dict(m_user=z(uw), v_user=z(uw), m_item=z(iw), v_item=z(iw), g_user=z(uw), g_item=z(iw))
-        self.MF_optimizer.adam_state = ops.new_adam_state(self.device)
+        # MF Adam is dense in the reference (model/transfer.py:392); by default the bit-identical row-lazy form of it
+        # runs (ops.adam_rows: only the batch rows move per step, every row once per epoch); SML_DENSE_ADAM=1 sweeps
+        self.lazy_adam = os.environ.get("SML_DENSE_ADAM", "0") != "1"
+        self.MF_optimizer.adam_state = ops.new_adam_state(self.device, history=self.lazy_adam)
+        self._stamps = {}
+        if self.lazy_adam:
+            self._stamps = dict(stamp_user=ops.new_row_stamps(uw.shape[0], self.MF_optimizer.adam_state),
+                                stamp_item=ops.new_row_stamps(iw.shape[0], self.MF_optimizer.adam_state))
         self.MF_optimizer.state = {self.MFbase.user_laten.weight: dict(exp_avg=self._mf["m_user"], exp_avg_sq=self._mf["v_user"]),
                                    self.MFbase.item_laten.weight: dict(exp_avg=self._mf["m_item"], exp_avg_sq=self._mf["v_item"])}
         th = self.transfer.theta
@@ -348,7 +356,7 @@ class meta_train(object):
                                       hat_user=uw, hat_item=iw, theta=self.transfer.theta, variant=self.transfer.variant,
                                       loss=ops.LOSS_BCE if self.transfer.variant == ops.VARIANT_COM else ops.LOSS_BPR,
                                       adam_state=self.MF_optimizer.adam_state, lr=lr, l2=args.l2, loss_out=self._loss,
-                                      workspace=ws, **self._mf)
+                                      workspace=ws, **self._mf, **self._stamps)
         self._tab_version += 1
         self._run_epoch("mf", build, (user, item, neg), n, B, (lr, args.l2, uw.data_ptr(), iw.data_ptr()))
         return self._loss[1].item() / nb
@@ -575,8 +583,10 @@ class meta_train(object):
             self._mf[k].copy_(v)
         for k, v in sd["tr_adam"].items():
             self._tr[k].copy_(v)
-        self.MF_optimizer.adam_state.copy_(sd["mf_adam_state"])
-        self.transfer_optimizer.adam_state.copy_(sd["tr_adam_state"])
+        self.MF_optimizer.adam_state[:2].copy_(sd["mf_adam_state"][:2])      # step counter + step scalars
+        self.transfer_optimizer.adam_state[:2].copy_(sd["tr_adam_state"][:2])
+        for st in self._stamps.values():                                     # every epoch ends flushed: all rows at step t
+            st.copy_(self.MF_optimizer.adam_state[0].to(torch.int32).expand_as(st))
         for k, v in sd["metrics"].items():
             setattr(self, k, list(v))
         if hasattr(self.dataset, "test_count"):

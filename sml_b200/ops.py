@@ -88,9 +88,21 @@ def transfer_forward(x_t, x_hat, theta_net, variant=VARIANT_COM, ids=None, norma
 
 
 # ------------------------------------------------------------------ optimizer
-def new_adam_state(device):
-    """[step, (step_size, sqrt(bc2)) packed as floats, spare, spare] -- see sml_adam_tick."""
-    return torch.zeros(4, dtype=torch.int64, device=device)
+ADAM_HISTORY = 4096
+
+
+def new_adam_state(device, history=False):
+    """[step, (step_size, sqrt(bc2)) packed as floats, history flag, spare] (+ ADAM_HISTORY slots holding the float pair
+    of every recent step when ``history``: what the row-lazy update replays) -- see sml_adam_tick."""
+    st = torch.zeros(4 + (ADAM_HISTORY if history else 0), dtype=torch.int64, device=device)
+    if history:
+        st[2] = 1
+    return st
+
+
+def new_row_stamps(n_rows, state):
+    """int32 [n_rows] 'last Adam step applied' stamps, initialised to the state's current step (no sync)."""
+    return state[0].to(torch.int32).expand(n_rows).contiguous()
 
 
 def adam_tick(state, lr, beta1=0.9, beta2=0.999):
@@ -100,6 +112,25 @@ def adam_tick(state, lr, beta1=0.9, beta2=0.999):
 def adam_dense(p, m, v, g, state, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, zero_grad=True):
     check(lib().sml_adam_dense(ptr(p), ptr(m), ptr(v), ptr(g), p.numel(), ptr(state), beta1, beta2, eps, weight_decay,
                                int(bool(zero_grad)), stream()), "adam_dense")
+
+
+def _i32t(t, name):
+    if t.dtype != torch.int32 or not t.is_contiguous():
+        raise TypeError("%s must be a contiguous int32 tensor" % name)
+    return t
+
+
+def adam_rows(p, m, v, g, stamp, ids, state, apply, beta1=0.9, beta2=0.999, eps=1e-8):
+    """Row-lazy exact Adam on the listed rows: ``apply=False`` replays the zero-gradient steps they missed up to t-1,
+    ``apply=True`` also applies step t with the gradient rows of ``g`` (re-zeroed)."""
+    check(lib().sml_adam_rows(ptr(p), ptr(m), ptr(v), ptr(g), ptr(_i32t(stamp, "stamp")), ptr(_i64(ids, "ids")), ids.numel(), p.shape[0],
+                              ptr(state), int(bool(apply)), beta1, beta2, eps, stream()), "adam_rows")
+
+
+def adam_flush(p, m, v, stamp, state, beta1=0.9, beta2=0.999, eps=1e-8):
+    """Every row of the table up to the state's current step (row-lazy exact Adam)."""
+    check(lib().sml_adam_flush(ptr(p), ptr(m), ptr(v), ptr(_i32t(stamp, "stamp")), p.shape[0], ptr(state), beta1, beta2, eps, stream()),
+          "adam_flush")
 
 
 # ------------------------------------------------------------------ steps
@@ -117,7 +148,7 @@ def step_rows(batch):
 def make_step_args(*, user, item, neg, last_user, last_item, hat_user, hat_item, theta, variant=VARIANT_COM, loss=LOSS_BCE,
                    g_user=None, g_item=None, m_user=None, v_user=None, m_item=None, v_item=None, adam_state=None,
                    lr=0.0, l2=0.0, g_theta=None, m_theta=None, v_theta=None, loss_out=None, workspace=None, batch=None,
-                   table_pitch=0, n_users=None, n_items=None):
+                   table_pitch=0, n_users=None, n_items=None, stamp_user=None, stamp_item=None):
     a = StepArgs()
     B = user.numel() if batch is None else int(batch)
     a.user, a.item, a.neg, a.batch = ptr(_i64(user, "user")), ptr(_i64(item, "item")), ptr(_i64(neg, "neg")), B
@@ -132,17 +163,26 @@ def make_step_args(*, user, item, neg, last_user, last_item, hat_user, hat_item,
     a.m_user, a.v_user, a.m_item, a.v_item = ptr(m_user), ptr(v_user), ptr(m_item), ptr(v_item)
     a.adam_state, a.lr, a.l2 = ptr(adam_state), float(lr), float(l2)
     a.g_theta, a.m_theta, a.v_theta = ptr(g_theta), ptr(m_theta), ptr(v_theta)
+    a.stamp_user = ptr(stamp_user if stamp_user is None else _i32t(stamp_user, "stamp_user"))
+    a.stamp_item = ptr(stamp_item if stamp_item is None else _i32t(stamp_item, "stamp_item"))
     if workspace is None:
         workspace = step_workspace(B, user.device)
     a.loss_out, a.workspace, a.workspace_bytes = ptr(loss_out), ptr(workspace), workspace.numel()
     # keep the tensors alive as long as the struct
     a._keep = (user, item, neg, last_user, last_item, hat_user, hat_item, theta, g_user, g_item, m_user, v_user, m_item,
-               v_item, adam_state, g_theta, m_theta, v_theta, loss_out, workspace)
+               v_item, adam_state, g_theta, m_theta, v_theta, loss_out, workspace, stamp_user, stamp_item)
+    a._lazy = (hat_user, m_user, v_user, stamp_user, hat_item, m_item, v_item, stamp_item, adam_state) if stamp_user is not None else None
     return a
 
 
-def mf_step(args):
+def mf_step(args, flush=True):
+    """One MF step.  With row stamps in ``args`` (row-lazy Adam) the tables are flushed afterwards unless ``flush=False``
+    (then call ``adam_flush`` before reading them)."""
     check(lib().sml_mf_step(C.byref(args), stream()), "mf_step")
+    if flush and args._lazy is not None:
+        hu, mu, vu, su, hi, mi, vi, si, st = args._lazy
+        adam_flush(hu, mu, vu, su, st)
+        adam_flush(hi, mi, vi, si, st)
 
 
 def tr_step(args):
@@ -170,11 +210,14 @@ def pack_rows(tab, ids=None):
     return out
 
 
-def fullcat_ranks(user_tab, item_tab, users, pos_items, items_packed=None, item_id0=0, n_items=None, gt=None, eq=None):
+def fullcat_ranks(user_tab, item_tab, users, pos_items, items_packed=None, item_id0=0, n_items=None, gt=None, eq=None, s_pos=None):
     """Full-catalog rank counts of (users[n], pos_items[n]) against every row of item_tab (or of a pre-packed
-    item shard).  Returns (gt, eq) int32 [n]; pass gt/eq to accumulate over several item shards."""
+    item shard).  Returns (gt, eq) int32 [n]; pass gt/eq to accumulate over several item shards.  ``s_pos``: the
+    positive scores when the positive item rows are not in ``item_tab`` (row-sharded catalog); ``pos_items`` are then ids
+    in the shard's numbering (or -1: positive not in this shard)."""
     n = users.numel()
-    s_pos = pair_scores(user_tab, item_tab, users, pos_items) if items_packed is None or item_tab is not None else None
+    if s_pos is None:
+        s_pos = pair_scores(user_tab, item_tab, users, pos_items)
     up = pack_rows(user_tab, users)
     if items_packed is None:
         items_packed = pack_rows(item_tab)

@@ -63,6 +63,53 @@ class RowExchange(object):
         p.n = ids.numel()
         return p
 
+    def plan_epoch(self, ids, sizes):
+        """Plans for a whole epoch at once.  ``ids``: int64 [sum(sizes)], the ids this rank needs, step after step
+        (``sizes[s]`` of them at step s; the step count must be the same on every rank).  Returns one ExchangePlan per
+        step, equal to what ``plan`` would return for that step's ids -- but with ONE host synchronisation and two
+        all-to-alls per epoch instead of per step, so the steps themselves enqueue without ever waiting for the GPU."""
+        W, S = self.world, len(sizes)
+        dev = ids.device
+        starts = [0]
+        for n in sizes:
+            starts.append(starts[-1] + int(n))
+        if ids.numel() != starts[-1]:
+            raise ValueError("plan_epoch: ids has %d entries, sizes sum to %d" % (ids.numel(), starts[-1]))
+        step = torch.repeat_interleave(torch.arange(S, device=dev), torch.tensor(sizes, device=dev), output_size=starts[-1])
+        owner = ids % W
+        by_step = torch.argsort(step * W + owner, stable=True)            # per step: requests grouped by owner
+        inv = torch.empty_like(by_step)
+        inv[by_step] = torch.arange(ids.numel(), device=dev)
+        key = owner * S + step
+        by_owner = torch.argsort(key, stable=True)                        # per owner: steps in order (the send layout)
+        counts = torch.bincount(key, minlength=W * S).view(W, S)          # [owner, step]
+        if W > 1:
+            rc = torch.empty_like(counts)
+            dist.all_to_all_single(rc, counts.contiguous(), group=self.group)   # rc[r, s]: what rank r asks of me at step s
+        else:
+            rc = counts
+        both = torch.stack([counts, rc]).tolist()                         # the one host sync of the epoch
+        counts_h, rc_h = both
+        recv_all = self._a2a((ids // W)[by_owner], [sum(r) for r in counts_h], [sum(r) for r in rc_h])   # grouped (source, step)
+        n_recv = recv_all.numel()
+        src_step = torch.repeat_interleave(torch.arange(W * S, device=dev), rc.reshape(-1), output_size=n_recv)
+        regroup = torch.argsort((src_step % S) * W + src_step // S, stable=True)     # -> grouped (step, source)
+        recv_by_step = recv_all[regroup]
+        plans, r0 = [], 0
+        for s in range(S):
+            p = ExchangePlan()
+            a, b = starts[s], starts[s + 1]
+            p.order = by_step[a:b] - a
+            p.inverse = inv[a:b] - a
+            p.send_counts = [counts_h[r][s] for r in range(W)]
+            p.recv_counts = [rc_h[r][s] for r in range(W)]
+            nr = sum(p.recv_counts)
+            p.recv_loc = recv_by_step[r0:r0 + nr]
+            r0 += nr
+            p.n = b - a
+            plans.append(p)
+        return plans
+
     def fetch(self, plan, gather_fn):
         """gather_fn(local_rows) -> [m, W] rows of this rank's shard; returns [n, W] in the original id order."""
         mine = gather_fn(plan.recv_loc)
@@ -99,7 +146,12 @@ class ShardedSML(object):
         self.transfer = transfer
         self.m_theta, self.v_theta = z(transfer.theta), z(transfer.theta)
         dev = user_tab.device
-        self.mf_state, self.tr_state = ops.new_adam_state(dev), ops.new_adam_state(dev)
+        # MF Adam: the reference's dense update in its bit-identical row-lazy form (ops.adam_rows) -- per step only the
+        # rows the exchange touched move, the whole shard once per flush() -- instead of 7 table sweeps per step
+        self.mf_state, self.tr_state = ops.new_adam_state(dev, history=True), ops.new_adam_state(dev)
+        self.stamp_user = ops.new_row_stamps(user_tab.shape[0], self.mf_state)
+        self.stamp_item = ops.new_row_stamps(item_tab.shape[0], self.mf_state)
+        self._pending = 0
         self.mf_lr, self.l2, self.tr_lr, self.tr_l2 = mf_lr, l2, tr_lr, tr_l2
         self.loss = torch.zeros(2, dtype=torch.float32, device=dev)
         self._ws = {}
@@ -117,12 +169,15 @@ class ShardedSML(object):
         dist.all_reduce(t, group=self.group)
         return int(t.item())
 
-    def _forward_backward(self, user, item, neg, hat_u, hat_i, want_theta_grad):
-        """Exchange rows, run forward + loss + gradients on the received [last | hat] pairs."""
+    def _forward_backward(self, user, item, neg, hat_u, hat_i, want_theta_grad, live=False, plans=None):
+        """Exchange rows, run forward + loss + gradients on the received [last | hat] pairs.  ``live``: hat_* are the
+        live MF shards, whose requested rows first catch up with the zero-gradient Adam steps they missed."""
         ops = self.ops
         B = user.numel()
-        pu = self.ex.plan(user)
-        pi = self.ex.plan(torch.cat([item, neg]))
+        pu, pi = plans if plans is not None else (self.ex.plan(user), self.ex.plan(torch.cat([item, neg])))
+        if live:
+            ops.adam_rows(self.user, self.m_user, self.v_user, None, self.stamp_user, pu.recv_loc, self.mf_state, apply=False)
+            ops.adam_rows(self.item, self.m_item, self.v_item, None, self.stamp_item, pi.recv_loc, self.mf_state, apply=False)
         ru = self.ex.fetch(pu, lambda loc: ops.gather_pairs(self.last_user, hat_u, loc))      # [B, 128]
         ri = self.ex.fetch(pi, lambda loc: ops.gather_pairs(self.last_item, hat_i, loc))      # [2B, 128]
         ar = torch.arange(2 * B, dtype=torch.int64, device=user.device)
@@ -138,25 +193,69 @@ class ShardedSML(object):
         return pu, pi, d_rows, rp
 
     # ------------------------------------------------------------------ the two hot loops
-    def mf_step(self, user, item, neg):
+    def _epoch_plans(self, user, item, neg, B):
+        """Per-step exchange plans and global-batch scales for an epoch of this rank's triples (one host sync)."""
+        n = user.numel()
+        sizes = [min(B, n - o) for o in range(0, n, B)]
+        if self.world > 1:
+            t = torch.tensor(sizes, dtype=torch.int64, device=user.device)
+            dist.all_reduce(t, group=self.group)                   # global batch of every step (same step count everywhere)
+        pu = self.ex.plan_epoch(user, sizes)
+        it = torch.cat([torch.cat([item[o:o + b], neg[o:o + b]]) for o, b in zip(range(0, n, B), sizes)]) if n else item
+        pi = self.ex.plan_epoch(it, [2 * b for b in sizes])
+        glob = t.tolist() if self.world > 1 else sizes
+        return sizes, pu, pi, [b / g for b, g in zip(sizes, glob)]
+
+    def mf_epoch(self, user, item, neg, B):
+        """HOT LOOP A over this rank's triples, ``B`` per step: the exchange is planned once for the whole epoch, the
+        steps enqueue without host synchronisation.  Returns the summed (global-mean) step losses as a device scalar."""
+        sizes, pu, pi, scales = self._epoch_plans(user, item, neg, B)
+        total = torch.zeros((), dtype=torch.float32, device=user.device)
+        for s, b in enumerate(sizes):
+            o = s * B
+            total += self.mf_step(user[o:o + b], item[o:o + b], neg[o:o + b], plans=(pu[s], pi[s]), scale=scales[s])
+        return total
+
+    def tr_epoch(self, user, item, neg, B):
+        """HOT LOOP B over this rank's triples (see mf_epoch)."""
+        sizes, pu, pi, scales = self._epoch_plans(user, item, neg, B)
+        total = torch.zeros((), dtype=torch.float32, device=user.device)
+        for s, b in enumerate(sizes):
+            o = s * B
+            total += self.tr_step(user[o:o + b], item[o:o + b], neg[o:o + b], plans=(pu[s], pi[s]), scale=scales[s])
+        return total
+
+    def mf_step(self, user, item, neg, plans=None, scale=None):
         """HOT LOOP A body (model/transfer.py:463-511) on this rank's slice of the global batch."""
         ops = self.ops
         B = user.numel()
-        scale = B / self._global_batch(B)                      # BCE is a mean over the GLOBAL batch
-        pu, pi, d_rows, rp = self._forward_backward(user, item, neg, self.user, self.item, False)
+        if scale is None:
+            scale = B / self._global_batch(B)                  # BCE is a mean over the GLOBAL batch
+        if self._pending >= ops.ADAM_HISTORY - 2:
+            self.flush()                                       # the step-scalar history ring is about to wrap
+        ops.adam_tick(self.mf_state, self.mf_lr)
+        self._pending += 1
+        pu, pi, d_rows, rp = self._forward_backward(user, item, neg, self.user, self.item, False, live=True, plans=plans)
         self.ex.push(pu, d_rows[:B], lambda loc, g: ops.scatter_grads(self.g_user, self.user, loc, g.contiguous(), scale, self.l2))
         self.ex.push(pi, d_rows[rp:rp + 2 * B], lambda loc, g: ops.scatter_grads(self.g_item, self.item, loc, g.contiguous(), scale, self.l2))
-        ops.adam_tick(self.mf_state, self.mf_lr)
-        ops.adam_dense(self.user, self.m_user, self.v_user, self.g_user, self.mf_state)
-        ops.adam_dense(self.item, self.m_item, self.v_item, self.g_item, self.mf_state)
+        ops.adam_rows(self.user, self.m_user, self.v_user, self.g_user, self.stamp_user, pu.recv_loc, self.mf_state, apply=True)
+        ops.adam_rows(self.item, self.m_item, self.v_item, self.g_item, self.stamp_item, pi.recv_loc, self.mf_state, apply=True)
         return self.loss[0] * scale
 
-    def tr_step(self, user, item, neg):
+    def flush(self):
+        """Bring every row of the live shards up to the current Adam step (before they are read as a whole)."""
+        if self._pending:
+            self.ops.adam_flush(self.user, self.m_user, self.v_user, self.stamp_user, self.mf_state)
+            self.ops.adam_flush(self.item, self.m_item, self.v_item, self.stamp_item, self.mf_state)
+            self._pending = 0
+
+    def tr_step(self, user, item, neg, plans=None, scale=None):
         """HOT LOOP B body (model/transfer.py:701-728): theta gradients, all-reduced, replicated Adam."""
         ops = self.ops
         B = user.numel()
-        scale = B / self._global_batch(B)
-        self._forward_backward(user, item, neg, self.user_hat, self.item_hat, True)
+        if scale is None:
+            scale = B / self._global_batch(B)
+        self._forward_backward(user, item, neg, self.user_hat, self.item_hat, True, plans=plans)
         g = self.transfer.theta_grad
         if scale != 1.0:
             g.mul_(scale)
@@ -168,14 +267,17 @@ class ShardedSML(object):
 
     # ------------------------------------------------------------------ row-local pieces
     def save_last(self):
+        self.flush()
         self.last_user.copy_(self.user); self.last_item.copy_(self.item)
 
     def save_hat(self):
+        self.flush()
         self.user_hat.copy_(self.user); self.item_hat.copy_(self.item)
 
     def updata(self):
         """model/transfer.py:884-902 on the local shard: no communication."""
         ops = self.ops
+        self.flush()            # nothing pending survives the overwrite below; stamps end at the current step
         th = self.transfer.theta
         ops.transfer_forward(self.last_user, self.user_hat, th[:ops.NET_STRIDE], variant=self.transfer.variant, out=self.user)
         ops.transfer_forward(self.last_item, self.item_hat, th[ops.NET_STRIDE:], variant=self.transfer.variant, out=self.item)
@@ -184,6 +286,7 @@ class ShardedSML(object):
         """Candidate evaluation of this rank's slice of a test file: user rows come through the exchange, the
         (small) item table is all-gathered once; returns global (hits, ndcg_sum, n)."""
         ops = self.ops
+        self.flush()
         dev = rows.device
         n = rows.shape[0]
         pu = self.ex.plan(rows[:, 0].contiguous())
@@ -205,5 +308,57 @@ class ShardedSML(object):
         hits, nd = ops.eval_reduce(gt, eq, topK, batch=max(n, 1))
         out = torch.stack([hits.sum().float(), nd.sum(), torch.tensor(float(n), device=dev)])
         if self.world > 1:
+            dist.all_reduce(out, group=self.group)
+        return out
+
+    def eval_fullcat(self, pairs, topK, chunk=1 << 16):
+        """Full-catalog recall / NDCG@K (BASELINE.json config 5) of this rank's slice of evaluated (user, positive item)
+        pairs against the WHOLE row-sharded catalog: user rows and positive-item rows come through the exchange, the
+        positive score is computed once (fp32 FFMA, ops.pair_scores), every rank ranks all pairs against its own item
+        shard with the tcgen05 score GEMM (ops.fullcat_ranks) and the per-pair counts add up with one all-reduce.
+        Returns global (hits, ndcg_sum, n) like eval_candidates."""
+        ops = self.ops
+        self.flush()
+        dev = pairs.device
+        W, R = self.world, self.rank
+        n = pairs.shape[0]
+        nmax = n
+        if W > 1:
+            t = torch.tensor([n], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            nmax = int(t.item())
+        items_pk = ops.pack_rows(self.item)                      # this rank's item shard as a tensor-core operand
+        out = torch.zeros(3, dtype=torch.float32, device=dev)
+        for c0 in range(0, max(nmax, 1), chunk):
+            sl = pairs[c0:c0 + chunk]
+            m = sl.shape[0]
+            mmax = min(chunk, nmax - c0)
+            users, pos = sl[:, 0].contiguous(), sl[:, 1].contiguous()
+            ur = self.ex.fetch(self.ex.plan(users), lambda loc: self.user[loc])
+            pr = self.ex.fetch(self.ex.plan(pos), lambda loc: self.item[loc])
+            ar = torch.arange(m, dtype=torch.int64, device=dev)
+            sp = ops.pair_scores(ur.contiguous(), pr.contiguous(), ar, ar) if m else torch.empty(0, device=dev)
+            if W > 1:       # every rank ranks every pair of the chunk against its own item shard
+                pad_u = torch.zeros(mmax, 64, device=dev); pad_u[:m] = ur
+                pad_s = torch.full((mmax,), float("inf"), device=dev); pad_s[:m] = sp
+                pad_p = torch.full((mmax,), -1, dtype=torch.int64, device=dev); pad_p[:m] = pos
+                all_u = torch.empty(W * mmax, 64, device=dev); dist.all_gather_into_tensor(all_u, pad_u, group=self.group)
+                all_s = torch.empty(W * mmax, device=dev); dist.all_gather_into_tensor(all_s, pad_s, group=self.group)
+                all_p = torch.empty(W * mmax, dtype=torch.int64, device=dev); dist.all_gather_into_tensor(all_p, pad_p, group=self.group)
+            else:
+                all_u, all_s, all_p = ur.contiguous(), sp, pos
+            if all_u.shape[0] == 0:
+                continue
+            local_pos = torch.where((all_p >= 0) & (all_p % W == R), all_p // W, torch.full_like(all_p, -1))
+            ar_all = torch.arange(all_u.shape[0], dtype=torch.int64, device=dev)
+            gt, eq = ops.fullcat_ranks(all_u, None, ar_all, local_pos, items_packed=items_pk, n_items=self.item.shape[0], s_pos=all_s)
+            if W > 1:
+                cnt = torch.stack([gt, eq])
+                dist.all_reduce(cnt, group=self.group)
+                gt, eq = cnt[0, R * mmax:R * mmax + m].contiguous(), cnt[1, R * mmax:R * mmax + m].contiguous()
+            if m:
+                hits, nd = ops.eval_reduce(gt, eq, topK, batch=m)
+                out += torch.stack([hits.sum().float(), nd.sum(), torch.tensor(float(m), device=dev)])
+        if W > 1:
             dist.all_reduce(out, group=self.group)
         return out

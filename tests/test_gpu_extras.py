@@ -82,3 +82,69 @@ def test_baseline_trainers_learn():
         last = t.run_period(periods[1][0], epochs=6)[-1]
         r1, _ = t.test(periods[1][1], topK=10)
         assert last < first and r1 > r0 + 0.05, (cls.__name__, first, last, r0, r1)
+
+
+def test_row_lazy_adam_is_bit_identical_to_the_dense_sweep():
+    """ops.adam_rows / adam_flush replay the zero-gradient steps a row missed: after a flush the table, exp_avg and
+    exp_avg_sq must equal the dense sweep (model/transfer.py:392, dense torch.optim.Adam over nn.Embedding) bit for bit,
+    and a row read right after its catch-up must equal the dense row before that step's update."""
+    from sml_b200 import ops
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    N, T, K = 3000, 45, 257
+    p0 = torch.randn(N, 64, generator=gen).to(dev)
+    pd, md, vd, gd = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0), torch.zeros_like(p0)
+    pl, ml, vl, gl = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0), torch.zeros_like(p0)
+    sd, sl = ops.new_adam_state(dev), ops.new_adam_state(dev, history=True)
+    stamp = ops.new_row_stamps(N, sl)
+    for t in range(T):
+        # Zipf-ish ids with duplicates; a third of the table never appears
+        ids = (torch.rand(K, generator=gen) ** 3 * (2 * N // 3)).long().to(dev)
+        grads = (torch.randn(K, 64, generator=gen) * 0.1).to(dev)
+        ops.adam_tick(sd, 0.01); ops.adam_tick(sl, 0.01)
+        ops.adam_rows(pl, ml, vl, None, stamp, ids, sl, apply=False)
+        assert torch.equal(pl[ids], pd[ids]), "step %d: caught-up rows differ from the dense table" % t
+        u, inv = torch.unique(ids, return_inverse=True)          # deterministic duplicate sum, same for both arms
+        acc = torch.zeros(u.numel(), 64, device=dev).index_add_(0, inv, grads)
+        gd[u] = acc; gl[u] = acc
+        ops.adam_dense(pd, md, vd, gd, sd)
+        ops.adam_rows(pl, ml, vl, gl, stamp, ids, sl, apply=True)
+        assert float(gl.abs().max()) == 0.0 and float(gd.abs().max()) == 0.0
+        if t == 20:
+            ops.adam_flush(pl, ml, vl, stamp, sl)
+            assert torch.equal(pl, pd)
+    ops.adam_flush(pl, ml, vl, stamp, sl)
+    assert torch.equal(pl, pd) and torch.equal(ml, md) and torch.equal(vl, vd)
+    assert int(stamp.min()) == T and int(stamp.max()) == T
+
+
+def test_mf_epoch_row_lazy_adam_matches_dense():
+    """sml_mf_epoch with row stamps (row-lazy exact Adam + flush) against the same epoch with the dense sweeps."""
+    from sml_b200 import ops
+    from sml_b200.model.conv_transfer import ConvTransfer_com
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    U, I, B, n = 5000, 9000, 256, 256 * 9 + 100
+    tr = ConvTransfer_com(64, 64).to(dev)
+    lu, li = torch.randn(U, 64, device=dev) * 0.3, torch.randn(I, 64, device=dev) * 0.3
+    hu0, hi0 = lu + 0.05 * torch.randn_like(lu), li + 0.05 * torch.randn_like(li)
+    user, item, neg = torch.randint(0, U, (n,), device=dev), torch.randint(0, I, (n,), device=dev), torch.randint(0, I, (n,), device=dev)
+    out = []
+    for lazy in (False, True):
+        hu, hi = hu0.clone(), hi0.clone()
+        z = {k: torch.zeros_like(hu if "user" in k else hi) for k in ("g_user", "m_user", "v_user", "g_item", "m_item", "v_item")}
+        st = ops.new_adam_state(dev, history=lazy)
+        if lazy:
+            z.update(stamp_user=ops.new_row_stamps(U, st), stamp_item=ops.new_row_stamps(I, st))
+        loss = torch.zeros(2, device=dev)
+        a = ops.make_step_args(user=user, item=item, neg=neg, batch=B, last_user=lu, last_item=li, hat_user=hu, hat_item=hi,
+                               theta=tr.theta, adam_state=st, lr=0.01, l2=1e-6, loss_out=loss, **z)
+        for _ in range(2):
+            ops.mf_epoch(a, n)
+        out.append((hu, hi, z["m_user"], z["v_item"], loss.clone(), int(st[0])))
+    d, l = out
+    assert d[5] == l[5] == 2 * 10
+    # the gradient scatter uses fp32 atomics (duplicate ids), so the two runs agree to rounding, not bitwise
+    for x, y in zip(d[:4], l[:4]):
+        assert (x - y).abs().max().item() < 2e-6
+    assert abs(float(d[4][1] - l[4][1])) < 1e-4 * abs(float(d[4][1]))

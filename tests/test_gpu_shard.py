@@ -35,6 +35,7 @@ def test_sharded_steps_world1_match_fused_steps():
     s = ShardedSML(T(ut, dev), T(it, dev), m2, world=1, rank=0, mf_lr=0.01, l2=1e-6, tr_lr=0.001, tr_l2=1e-4)
     l2 = s.mf_step(T(ids[0], dev), T(ids[1], dev), T(ids[2], dev))
     assert abs(float(l2) + 0.0 - (loss[0].item() - 1e-6 * 0.5 * float((ut[ids[0]] ** 2).sum() + (it[ids[1]] ** 2).sum() + (it[ids[2]] ** 2).sum()))) < 2e-5
+    s.flush()
     assert (s.user - u1).abs().max().item() < 2e-6 and (s.item - i1).abs().max().item() < 2e-6
     # transfer step
     s.save_hat()
@@ -53,3 +54,37 @@ def test_sharded_steps_world1_match_fused_steps():
     out = s.eval_candidates(rows, 5)
     gt, eq = ops.eval_candidates(s.user, s.item, rows)
     assert int(out[0]) == int(((gt + eq) < 5).sum()) and int(out[2]) == 64
+    # full-catalog ranks through the sharded path == the single-GPU full-catalog kernel
+    pairs = T(np.stack([rng.integers(0, U, 90), rng.integers(0, I, 90)], 1).astype(np.int64), dev)
+    fc = s.eval_fullcat(pairs, 20, chunk=64)                     # two chunks
+    g1, e1 = ops.fullcat_ranks(s.user, s.item, pairs[:, 0].contiguous(), pairs[:, 1].contiguous())
+    h1, n1 = ops.eval_reduce(g1, e1, 20, batch=90)
+    assert int(fc[0]) == int(h1.sum()) and int(fc[2]) == 90 and abs(float(fc[1]) - float(n1.sum())) < 1e-4
+
+
+def test_sharded_epoch_api_matches_step_api():
+    """mf_epoch / tr_epoch (exchange planned once per epoch) == the same steps planned one by one."""
+    from sml_b200.shard import ShardedSML
+    from tests.test_gpu_parity import make_module, T
+    from sml_b200.model.conv_transfer import ConvTransfer_com
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(4)
+    U, I, B, n = 400, 700, 96, 96 * 3 + 17
+    ut = rng.standard_normal((U, 64)).astype(np.float32) * 0.3; it = rng.standard_normal((I, 64)).astype(np.float32) * 0.3
+    tu, ti = O.init_theta(np.random.default_rng(1)), O.init_theta(np.random.default_rng(2))
+    u, i, j = (T(rng.integers(0, k, n).astype(np.int64), dev) for k in (U, I, I))
+    res = []
+    for epoch_api in (False, True):
+        s = ShardedSML(T(ut, dev), T(it, dev), make_module(ConvTransfer_com, tu, ti, dev), world=1, rank=0)
+        s.user.add_(0.05); s.save_hat(); s.user.sub_(0.05)
+        if epoch_api:
+            lm = s.mf_epoch(u, i, j, B); lt = s.tr_epoch(u, i, j, B)
+        else:
+            lm = sum(s.mf_step(u[o:o + B], i[o:o + B], j[o:o + B]) for o in range(0, n, B))
+            lt = sum(s.tr_step(u[o:o + B], i[o:o + B], j[o:o + B]) for o in range(0, n, B))
+        s.flush()
+        res.append((s.user.clone(), s.item.clone(), s.transfer.theta.clone(), float(lm), float(lt)))
+    a, b = res
+    assert (a[0] - b[0]).abs().max().item() < 2e-6 and (a[1] - b[1]).abs().max().item() < 2e-6
+    assert (a[2] - b[2]).abs().max().item() < 1e-5
+    assert abs(a[3] - b[3]) < 1e-4 * abs(a[3]) and abs(a[4] - b[4]) < 1e-4 * abs(a[4])

@@ -218,3 +218,22 @@ def test_memory_stream_branches():
     ds.reinit(); assert ds.test_count == 0
     stop = MemoryStream(periods, 10, 20, online_train_time=1, online_test_time=4, tr_stop=True)
     assert stop.next_train(2)[1] is None
+
+
+def test_select_neg_forinteraction_matches_reference(golden, tmp_path):
+    """Test-file builder (data/dataset2.py:356-414): same files as the reference for the same np.random.seed."""
+    from sml_b200.data.dataset2 import select_neg_forinteraction
+    g = golden("select_neg")
+    base = tmp_path / "mini"
+    base.mkdir()
+    for k in range(5):
+        np.save(str(base / ("%d.npy" % k)), g["file%d" % k])
+    np.random.seed(int(g["seed"]))
+    out = select_neg_forinteraction(path=str(tmp_path) + "/", datasetname="mini", file_path_list=[str(k) for k in range(5)],
+                                    leave_for_init_train=float(g["leave"]), neg_num=int(g["neg_num"]))
+    assert len(out) == 2
+    for k, t in zip((3, 4), out):
+        assert np.array_equal(t, g["test%d" % k])
+        assert np.array_equal(np.load(str(base / "test" / ("%d.npy" % k))), g["test%d" % k])
+        # the defining properties: negatives distinct, never the row's own history
+        assert all(len(set(r[2:])) == int(g["neg_num"]) and r[1] not in r[2:] for r in t)

@@ -38,6 +38,19 @@ def _worker(rank, world, port, out_dir):
         acc = torch.zeros_like(shard)
         ex.push(plan, grads, lambda loc, rows: acc.index_add_(0, loc, rows))
         torch.save(dict(ids=ids, grads=grads, acc=acc), os.path.join(out_dir, "r%d.pt" % rank))
+        # whole-epoch planning: per-step plans identical to planning every step on its own (ragged last step)
+        sizes = [11, 11, 11, 4 + rank]
+        eids = torch.randint(0, N, (sum(sizes),), generator=gi)
+        eids[11:15] = eids[11]
+        plans = ex.plan_epoch(eids, sizes)
+        o = 0
+        for s_, p_ in zip(sizes, plans):
+            one = ex.plan(eids[o:o + s_])
+            assert torch.equal(p_.order, one.order) and torch.equal(p_.inverse, one.inverse)
+            assert p_.send_counts == one.send_counts and p_.recv_counts == one.recv_counts
+            assert torch.equal(p_.recv_loc, one.recv_loc) and p_.n == one.n
+            assert torch.equal(ex.fetch(p_, lambda loc: shard[loc]), full[eids[o:o + s_]])
+            o += s_
         # empty request from one rank must not dead-lock
         plan2 = ex.plan(ids[:0] if rank == 0 else ids[:3])
         got2 = ex.fetch(plan2, lambda loc: shard[loc])
@@ -68,3 +81,6 @@ def test_row_exchange_world1_identity():
     acc = torch.zeros_like(full)
     ex.push(plan, torch.ones(4, 4), lambda loc, rows: acc.index_add_(0, loc, rows))
     assert acc[3, 0] == 2 and acc[9, 0] == 1 and acc[1, 0] == 0
+    plans = ex.plan_epoch(torch.tensor([3, 3, 9, 0, 7]), [2, 2, 1])
+    assert [p.n for p in plans] == [2, 2, 1]
+    assert torch.equal(ex.fetch(plans[1], lambda loc: full[loc]), full[torch.tensor([9, 0])])
