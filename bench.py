@@ -362,6 +362,23 @@ def run_ours(a):
     per_eval_ms = ev_ms / max(ev_n, 1)
     ach = shape["rows"] * EVAL_BYTES_PER_ROW / max(per_eval_ms, 1e-9) / 1e6
     value = world * K / dev_s
+    # every phase of the period against the roofline that bounds it: fp32-equivalent FLOP of the transfer net
+    # (403 456 per row forward; x2 with the data gradient, x3 with the weight gradients) over the phase's device time
+    mf_steps, tr_steps, n_updata, _ = period_counts(shape["rows"])
+    ph_ms = {k: v[1] / K for k, v in phases.items()}
+    tf32_peak = float(peaks.get("bf16_tflops", 2250.0)) / 2.0        # dense tf32 = half the bf16 rate; 3xTF32 issues 3 MMAs per product
+    def tensor_phase(rows, passes, ms):
+        tf = rows * TRANSFER_FLOP_PER_ROW * passes / max(ms, 1e-9) / 1e9
+        return {"bound": "tensor", "achieved": tf, "unit": "TFLOP/s fp32-equivalent", "peak": tf32_peak / 3.0, "frac": tf / (tf32_peak / 3.0)}
+    roofline_phases = {
+        "tr_epoch": dict(tensor_phase(3 * shape["rows"] * HYPER["TR_epochs"] * HYPER["multi_num"], 3, ph_ms.get("tr_epoch", 0.0)),
+                         us_per_step=ph_ms.get("tr_epoch", 0.0) / tr_steps * 1e3,
+                         note="768 rows per step: 24-30 CTAs per GEMM, bound by launch latency and per-SM L2 bandwidth, not by the tensor pipe"),
+        "mf_epoch": dict(tensor_phase(3 * shape["rows"] * HYPER["MF_epochs"] * HYPER["multi_num"], 2, ph_ms.get("mf_epoch", 0.0)),
+                         us_per_step=ph_ms.get("mf_epoch", 0.0) / mf_steps * 1e3),
+        "updata": tensor_phase((U + I) * n_updata, 1, ph_ms.get("updata", 0.0)),
+        "eval": {"bound": "hbm", "achieved": ach, "unit": "GB/s", "peak": hbm_peak, "frac": ach / hbm_peak},
+    }
     out = {
         "metric": "periods/sec", "value": value, "unit": "periods/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": dev_s / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -381,6 +398,7 @@ def run_ours(a):
         "phases_ms_per_period": {k: v[1] / K for k, v in phases.items()},
         "phase_counts_per_period": {k: v[0] / K for k, v in phases.items()},
         "kernels": kern,
+        "roofline_phases": roofline_phases,
         "roofline": {"kernel": "k_eval_candidates", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                      "frac": ach / hbm_peak, "traffic": EVAL_NCU_DRAM_BYTES if shape["rows"] == 75000 else None, "peak_source": peak_src,
                      "note": "algorithmic bytes = 264264 B x rows per launch (19.8 GB); the 31 MB item table is L2 resident "

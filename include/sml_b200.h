@@ -254,6 +254,15 @@ int64_t sml_host_rejection_walk(const int64_t *draws_host, int64_t n_draws, cons
  * with GELU applied on load, 2 A[k][m], 3 A[k][m] + GELU.  b_mode: 0 B[n][k], 1 B[k][n], 2 B[k][n] + GELU.
  * epi: 0 store, 1 + bias[n], 2 * GELU'(aux[m][n]), 3 accumulate into C.  tensor_cores != 0 selects the
  * tcgen05 3xTF32 kernel (bn = 64 | 128, optional transposed store C[n][m]), 0 the SIMT fp32 kernel. */
+/* Profiling aid (tools/tr_breakdown.py): bit mask that drops stages of sml_tr_step / sml_mf_step so that the critical
+ * path can be measured by difference.  1: no weight gradients, 2: no dA / conv backward, 4: nothing after the loss,
+ * 8: nothing after fc2, 64: no optimizer update, 128: nothing after fc1, 256: nothing after the conv prologue, 512: no 128 x 64 tiles for small batches.
+ * Results are garbage unless the mask is 0 (the default) or 512.  Returns the previous mask. */
+int sml_debug_set_mask(int mask);
+int sml_debug_mask(void);
+/* Tuning aid: override the split-K factors of the step GEMMs (fc2, d1, dW2, dW1); 0 = built-in choice. */
+int sml_debug_set_ksplit(int fc2, int d1, int w2, int w1);
+int sml_debug_ksplit(int which);
 int sml_debug_gemm(const float *A, const float *B, const float *bias, const float *aux, float *C, int M, int N, int K, int lda,
                    int ldb, int ldc, int a_mode, int b_mode, int epi, int transpose_out, int bn, int tensor_cores, void *stream);
 

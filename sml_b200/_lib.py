@@ -66,6 +66,10 @@ _PROTOS = {
     "sml_gather_pairs": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "sml_scatter_grads": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _dbl, _dbl, _vp]),
     "sml_host_rejection_walk": (_i64, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
+    "sml_debug_set_mask": (_i32, [_i32]),
+    "sml_debug_mask": (_i32, []),
+    "sml_debug_set_ksplit": (_i32, [_i32, _i32, _i32, _i32]),
+    "sml_debug_ksplit": (_i32, [_i32]),
     "sml_debug_gemm": (_i32, [_vp, _vp, _vp, _vp, _vp] + [_i32] * 12 + [_vp]),
     "sml_plain_mf_grads": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }

@@ -66,7 +66,7 @@ __device__ __forceinline__ void conv_point(const ConvW &w, float x0, float x1, f
 // ---------------------------------------------------------------------------------------------
 template <int R>
 __global__ void __launch_bounds__(CONV_THREADS)
-k_conv_fwd(ConvParams P, float *__restrict__ A, uint8_t *__restrict__ Apk, float *__restrict__ rowsq) {
+k_conv_fwd(ConvParams P, float *__restrict__ A, uint8_t *__restrict__ Apk, float *__restrict__ rowsq, float *__restrict__ zero_y) {
     __shared__ ConvW sw;
     sml_pdl_wait();
     sml_pdl_trigger();
@@ -96,6 +96,7 @@ k_conv_fwd(ConvParams P, float *__restrict__ A, uint8_t *__restrict__ Apk, float
             const float q = warp_sum(x1[0] * x1[0] + x1[1] * x1[1]);
             if (lane == 0 && h0 == 0) rowsq[g.row0 + r] = q;
         }
+        if (zero_y) zero_y[(g.row0 + r) * SML_D + lane + 32 * h0] = 0.f;   // split-K fc2 accumulates into Y (no memset node in the chain)
         float *a = A ? A + (g.row0 + r) * SML_FC1_IN : nullptr;
 #pragma unroll
         {
@@ -137,21 +138,12 @@ k_conv_bwd(ConvBwdParams P, const float *__restrict__ dA, float l2, float *__res
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * CONV_WARPS + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * CONV_WARPS;
-    // per-thread partial parameter gradients: w2 [5][10], b2 [5], w1 [10][R], b1 [10]
-    float gw2[5][10], gb2[5], gw1[10][3], gb1[10];
+    // per-thread partial parameter gradients, flat in the order of s_acc:
+    //   [0,50) w2[m][c]   [50,55) b2[m]   [55, 55+10R) w1[c][r]   [85,95) b1[c]   (95: padding)
+    float acc[96];
     if (THETA) {
 #pragma unroll
-        for (int m = 0; m < 5; ++m) {
-            gb2[m] = 0.f;
-#pragma unroll
-            for (int c = 0; c < 10; ++c) gw2[m][c] = 0.f;
-        }
-#pragma unroll
-        for (int c = 0; c < 10; ++c) {
-            gb1[c] = 0.f;
-#pragma unroll
-            for (int r = 0; r < 3; ++r) gw1[c][r] = 0.f;
-        }
+        for (int i = 0; i < 96; ++i) acc[i] = 0.f;
     }
     // two warps per row: warp 2r+h converts latent dims [32h, 32h+32) (both load the whole row for the norm)
     for (int64_t wr = warp0; wr < 2 * g.n; wr += nwarps) {
@@ -187,18 +179,18 @@ k_conv_bwd(ConvBwdParams P, const float *__restrict__ dA, float l2, float *__res
                 const float dz1 = dh * sml_gelu_grad(z1[c]);
                 dx1 = fmaf(sw.w1[c][1], dz1, dx1);
                 if (THETA) {
-                    gb1[c] += dz1;
-                    gw1[c][0] = fmaf(dz1, x0h, gw1[c][0]);
-                    gw1[c][1] = fmaf(dz1, x1h, gw1[c][1]);
-                    if (R == 3) gw1[c][2] = fmaf(dz1, x2h, gw1[c][2]);
+                    acc[85 + c] += dz1;
+                    acc[55 + c * R + 0] = fmaf(dz1, x0h, acc[55 + c * R + 0]);
+                    acc[55 + c * R + 1] = fmaf(dz1, x1h, acc[55 + c * R + 1]);
+                    if (R == 3) acc[55 + c * R + 2] = fmaf(dz1, x2h, acc[55 + c * R + 2]);
                 }
             }
             if (THETA) {
 #pragma unroll
                 for (int m = 0; m < 5; ++m) {
-                    gb2[m] += dz2[m];
+                    acc[50 + m] += dz2[m];
 #pragma unroll
-                    for (int c = 0; c < 10; ++c) gw2[m][c] = fmaf(dz2[m], h1[c], gw2[m][c]);
+                    for (int c = 0; c < 10; ++c) acc[m * 10 + c] = fmaf(dz2[m], h1[c], acc[m * 10 + c]);
                 }
             }
             if (MODE == 0) {
@@ -210,27 +202,24 @@ k_conv_bwd(ConvBwdParams P, const float *__restrict__ dA, float l2, float *__res
         }
     }
     if (THETA) {
-        // warp tree -> shared -> one global atomic per parameter per CTA
-#pragma unroll
-        for (int m = 0; m < 5; ++m) {
-#pragma unroll
-            for (int c = 0; c < 10; ++c) {
-                const float v = warp_sum(gw2[m][c]);
-                if (lane == 0) atomicAdd(&s_acc[m * 10 + c], v);
-            }
-            const float v = warp_sum(gb2[m]);
-            if (lane == 0) atomicAdd(&s_acc[50 + m], v);
+        // transposed warp reduction: at every halving step a lane keeps one half of its values and hands the other half to
+        // its partner (96 -> 48 -> 24 -> 12 -> 6 -> 3 values, 93 shuffles instead of 95 five-step butterflies); lane L ends
+        // with the full 32-lane sums of 3 parameters, then shared -> one global atomic per parameter per CTA
+#define SML_HALVE(N_, OFF_)                                                        \
+        {                                                                          \
+            const bool up = (lane & OFF_) != 0;                                    \
+            _Pragma("unroll") for (int i = 0; i < N_; ++i) {                       \
+                const float send = up ? acc[i] : acc[i + N_];                      \
+                const float keep = up ? acc[i + N_] : acc[i];                      \
+                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF_);          \
+            }                                                                      \
         }
+        SML_HALVE(48, 16) SML_HALVE(24, 8) SML_HALVE(12, 4) SML_HALVE(6, 2) SML_HALVE(3, 1)
+#undef SML_HALVE
+        const int base = ((lane & 16) ? 48 : 0) + ((lane & 8) ? 24 : 0) + ((lane & 4) ? 12 : 0) + ((lane & 2) ? 6 : 0) + ((lane & 1) ? 3 : 0);
 #pragma unroll
-        for (int c = 0; c < 10; ++c) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const float v = warp_sum(gw1[c][r]);
-                if (lane == 0) atomicAdd(&s_acc[55 + c * R + r], v);
-            }
-            const float v = warp_sum(gb1[c]);
-            if (lane == 0) atomicAdd(&s_acc[85 + c], v);
-        }
+        for (int j = 0; j < 3; ++j)
+            if (base + j < 95) atomicAdd(&s_acc[base + j], acc[j]);
         __syncthreads();
         float *gt = bg.g_theta;
         for (int i = threadIdx.x; i < 95; i += blockDim.x) {
@@ -253,7 +242,7 @@ __global__ void __launch_bounds__(LOSS_THREADS)
 k_loss(const float *__restrict__ Y, const float *__restrict__ rowsq, int64_t B, int64_t rowP, int64_t rowN, int loss_kind,
        int normalize_user, float l2, float *__restrict__ dY, uint8_t *__restrict__ dYpk, float *__restrict__ scores,
        float *__restrict__ loss_out, float *__restrict__ partials, unsigned int *__restrict__ ticket,
-       float *__restrict__ gb_user, float *__restrict__ gb_item) {
+       float *__restrict__ gb_user, float *__restrict__ gb_item, float *__restrict__ zero_dA) {
     __shared__ float s_part[LOSS_WARPS][3];
     __shared__ float s_gb[2][SML_D];
     sml_pdl_wait();
@@ -266,6 +255,14 @@ k_loss(const float *__restrict__ Y, const float *__restrict__ rowsq, int64_t B, 
     const float invB = 1.0f / (float)B;
     for (int64_t b = (int64_t)blockIdx.x * LOSS_WARPS + w; b < B; b += (int64_t)gridDim.x * LOSS_WARPS) {
         const float *yu = Y + b * SML_D, *yi = Y + (rowP + b) * SML_D, *yj = Y + (rowN + b) * SML_D;
+        if (zero_dA) {                                       // split-K d1 accumulates into dA (no memset node in the chain)
+#pragma unroll
+            for (int k = 0; k < SML_FC1_IN; k += 32) {
+                zero_dA[b * SML_FC1_IN + k + lane] = 0.f;
+                zero_dA[(rowP + b) * SML_FC1_IN + k + lane] = 0.f;
+                zero_dA[(rowN + b) * SML_FC1_IN + k + lane] = 0.f;
+            }
+        }
         float u[2] = {yu[lane], yu[lane + 32]};
         const float i_[2] = {yi[lane], yi[lane + 32]};
         const float j_[2] = {yj[lane], yj[lane + 32]};
@@ -366,7 +363,7 @@ int grid_for_rows(int64_t max_n) {
 }  // namespace
 
 int sml_launch_conv_fwd(const SmlRowGroup *groups, int n_groups, int variant, float *A, uint8_t *Apk, float *rowsq,
-                        cudaStream_t st) {
+                        cudaStream_t st, float *zero_y) {
     SML_REQUIRE(n_groups >= 1 && n_groups <= MAX_GROUPS, SML_E_BADARG, "conv_fwd: bad group count %d", n_groups);
     ConvParams P;
     P.n_groups = n_groups;
@@ -374,8 +371,8 @@ int sml_launch_conv_fwd(const SmlRowGroup *groups, int n_groups, int variant, fl
     for (int i = 0; i < n_groups; ++i) { P.g[i] = groups[i]; if (groups[i].n > max_n) max_n = groups[i].n; }
     if (max_n == 0) return SML_OK;
     dim3 grid(grid_for_rows(max_n), n_groups);
-    if (variant == SML_VARIANT_COM) SML_CUDA_OK(sml_launch(k_conv_fwd<3>, grid, dim3(CONV_THREADS), 0, st, P, A, Apk, rowsq));
-    else SML_CUDA_OK(sml_launch(k_conv_fwd<2>, grid, dim3(CONV_THREADS), 0, st, P, A, Apk, rowsq));
+    if (variant == SML_VARIANT_COM) SML_CUDA_OK(sml_launch(k_conv_fwd<3>, grid, dim3(CONV_THREADS), 0, st, P, A, Apk, rowsq, zero_y));
+    else SML_CUDA_OK(sml_launch(k_conv_fwd<2>, grid, dim3(CONV_THREADS), 0, st, P, A, Apk, rowsq, zero_y));
     SML_LAUNCH_OK();
     return SML_OK;
 }
@@ -397,6 +394,7 @@ int sml_launch_conv_bwd(const SmlConvBwdGroup *groups, int n_groups, int variant
     // fewer, fatter CTAs when parameter gradients are reduced (one atomic flush per CTA)
     int gx = grid_for_rows(max_n);
     // each CTA ends with 95 global atomics onto the same 95 parameters: a few dozen CTAs per group keep that cheap
+    // (96 per group measured 2-6 us slower per transfer step than 32, profiles/r01_tr_step_breakdown.md)
     if (theta) { const int cap = 32; if (gx > cap) gx = cap; }
     dim3 grid(gx, n_groups);
 #define SML_CB(R_, MODE_, TH_) SML_CUDA_OK(sml_launch(k_conv_bwd<R_, MODE_, TH_>, grid, dim3(CONV_THREADS), 0, st, P, dA, l2, d_rows))
@@ -415,11 +413,11 @@ int sml_launch_conv_bwd(const SmlConvBwdGroup *groups, int n_groups, int variant
 
 int sml_launch_loss(const float *Y, const float *rowsq, int64_t B, int64_t row_pos, int64_t row_neg, int loss_kind,
                     int normalize_user, float l2, float *dY, uint8_t *dYpk, float *scores, float *loss_out, float *partials,
-                    unsigned int *ticket, cudaStream_t st, float *gb_user, float *gb_item) {
+                    unsigned int *ticket, cudaStream_t st, float *gb_user, float *gb_item, float *zero_dA) {
     int64_t blocks = (B + LOSS_WARPS - 1) / LOSS_WARPS;
     if (blocks > 1024) blocks = 1024;   // partials[] holds 3 * 1024 floats
     SML_CUDA_OK(sml_launch(k_loss, dim3((unsigned)blocks), dim3(LOSS_THREADS), 0, st, Y, rowsq, B, row_pos, row_neg, loss_kind, normalize_user,
-                           l2, dY, dYpk, scores, loss_out, partials, ticket, gb_user, gb_item));
+                           l2, dY, dYpk, scores, loss_out, partials, ticket, gb_user, gb_item, zero_dA));
     SML_LAUNCH_OK();
     return SML_OK;
 }

@@ -64,6 +64,13 @@ extern "C" {
 
 int sml_abi_version(void) { return SML_ABI_VERSION; }
 
+static int g_debug_mask = 0;
+int sml_debug_set_mask(int mask) { const int old = g_debug_mask; g_debug_mask = mask; return old; }
+int sml_debug_mask(void) { return g_debug_mask; }
+static int g_debug_ks[4] = {0, 0, 0, 0};
+int sml_debug_set_ksplit(int fc2, int d1, int w2, int w1) { g_debug_ks[0] = fc2; g_debug_ks[1] = d1; g_debug_ks[2] = w2; g_debug_ks[3] = w1; return 0; }
+int sml_debug_ksplit(int which) { return (which >= 0 && which < 4) ? g_debug_ks[which] : 0; }
+
 const char *sml_last_error(void) { return g_err; }
 
 int sml_device_check(void) { return sml_check_device(); }

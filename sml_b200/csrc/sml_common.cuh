@@ -143,8 +143,9 @@ struct SmlRowGroup {
 
 // conv prologue: fc1 input for every row of the groups, as plain A[N,320] (or null) and/or as a packed
 // tensor-core operand Apk (umma_pack.cuh, 128-row tiles, or null); rowsq[n] = sum x_hat^2 (or null)
+// zero_y (optional): Y[N,64] rows of the groups are cleared (split-K fc2 accumulates into them)
 int sml_launch_conv_fwd(const SmlRowGroup *groups, int n_groups, int variant, float *A, uint8_t *Apk, float *rowsq,
-                        cudaStream_t st);
+                        cudaStream_t st, float *zero_y = nullptr);
 
 // conv backward.  dA [N,320].  mode 0: scatter (dx_hat + l2*x_hat) into g_tab rows (atomic);
 // mode 1: write dx_hat to d_rows [N,64];  theta_grad != null: accumulate conv1/conv2 grads.
@@ -181,7 +182,8 @@ int sml_launch_colsum(const SmlColsumProb *probs, int n_probs, cudaStream_t st);
 // gb_user / gb_item (optional): += column sums of dY over the user rows / the item rows (fc2 bias gradients)
 int sml_launch_loss(const float *Y, const float *rowsq, int64_t B, int64_t row_pos, int64_t row_neg, int loss_kind,
                     int normalize_user, float l2, float *dY, uint8_t *dYpk, float *scores, float *loss_out, float *partials,
-                    unsigned int *ticket, cudaStream_t st, float *gb_user = nullptr, float *gb_item = nullptr);
+                    unsigned int *ticket, cudaStream_t st, float *gb_user = nullptr, float *gb_item = nullptr,
+                    float *zero_dA = nullptr);   // zero_dA (optional): dA[N,320] rows of the batch are cleared (split-K d1)
 
 // tcgen05 GEMM with pre-packed operands (umma_packed.cu)
 enum { SML_PK_FC1 = 0, SML_PK_FC2 = 1, SML_PK_D2 = 2, SML_PK_D1 = 3 };

@@ -94,7 +94,10 @@ void make_groups(const sml_step_args *a, SmlRowGroup g[3]) {
 
 // K = 512 GEMMs (fc2, d1) of small batches have only a handful of output tiles: slice K so they cover more SMs
 // (measured: 119.3 -> 117.0 us for the B = 256 transfer step; at B = 1024 the atomics cost more than the slicing gains)
-int step_ksplit(const Rows &r) { return (r.user_tiles + r.item_tiles) <= 12 ? 4 : 1; }
+int step_ksplit(const Rows &r, int which = 0) {
+    if (sml_debug_ksplit(which) > 0) return sml_debug_ksplit(which);
+    return (r.user_tiles + r.item_tiles) <= 12 ? 4 : 1;
+}
 
 // two-net problem pair for the packed GEMMs
 void pk_pair(SmlPkProb out[2], const Rows &r, const uint8_t *A, int KC, size_t w_off, int N, const float *theta, size_t bias_off,
@@ -162,21 +165,24 @@ int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, b
         if (rc) return rc;
     }
     float *gbu2 = (tc && g_theta) ? g_theta + SML_OFF_F2B : nullptr, *gbi2 = (tc && g_theta) ? g_theta + SML_NET_STRIDE + SML_OFF_F2B : nullptr;
-    if (tc && step_ksplit(r) > 1)      // split-K slices accumulate into Y and dA
-        SML_CUDA_OK(cudaMemsetAsync(w.Y, 0, (size_t)((char *)w.dY - (char *)w.Y), st));
+    // split-K slices accumulate into Y (fc2) and dA (d1): the conv prologue and the loss kernel clear the batch rows on their
+    // way (a memset node in the chain would cost a launch and break the programmatic-dependent-launch overlap)
+    const bool zero_y = tc && step_ksplit(r, 0) > 1, zero_dA = tc && step_ksplit(r, 1) > 1;
     rc = sml_launch_conv_fwd(g, 3, a->variant, (!tc || need_plain_A) ? w.A : nullptr, tc ? w.Apk : nullptr,
-                             want_rowsq ? w.rowsq : nullptr, st);
+                             want_rowsq ? w.rowsq : nullptr, st, zero_y ? w.Y : nullptr);
     if (rc) return rc;
     if (ss) SML_CUDA_OK(cudaStreamWaitEvent(st, ss->join2, 0));
+    if (sml_debug_mask() & 256) return SML_OK;
     if (tc) {
         SmlPkProb p[2];
         // fc1: Z1 = A W1^T + b1 (conv_transfer.py:47); also emits GELU(Z1) packed for fc2
         pk_pair(p, r, w.Apk, 10, SML_PK_OFF_P1, 512, a->theta, SML_OFF_F1B, nullptr, w.Z1, 512, w.Gpk, w.theta_pk);
         rc = sml_launch_umma_packed(p, 2, SML_PK_FC1, st);
         if (rc) return rc;
+        if (sml_debug_mask() & 128) return SML_OK;
         // fc2: Y = GELU(Z1) W2^T + b2 (:48-49)
         pk_pair(p, r, w.Gpk, 16, SML_PK_OFF_P2, 64, a->theta, SML_OFF_F2B, nullptr, w.Y, 64, nullptr, w.theta_pk);
-        rc = sml_launch_umma_packed(p, 2, SML_PK_FC2, st, step_ksplit(r));
+        rc = sml_launch_umma_packed(p, 2, SML_PK_FC2, st, step_ksplit(r, 0));
         if (rc) return rc;
     } else {
         SmlGemmProb fc1[2] = {
@@ -190,9 +196,12 @@ int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, b
         rc = sml_launch_sgemm(fc2, 2, SML_A_MK_GELU, SML_B_NK, SML_EPI_BIAS, st);
         if (rc) return rc;
     }
+    const int dbg = sml_debug_mask();
+    if (dbg & 8) return SML_OK;
     rc = sml_launch_loss(w.Y, want_rowsq ? w.rowsq : nullptr, B, r.Bp, r.Bp + B, a->loss, a->variant == SML_VARIANT_CONV, l2, w.dY,
-                         tc ? w.dYpk : nullptr, scores, a->loss_out, w.partials, w.ticket, st, gbu2, gbi2);
+                         tc ? w.dYpk : nullptr, scores, a->loss_out, w.partials, w.ticket, st, gbu2, gbi2, zero_dA ? w.dA : nullptr);
     if (rc) return rc;
+    if (dbg & 4) return SML_OK;
     // dZ1 = (dY W2) * GELU'(Z1)
     if (tc) {
         SmlPkProb p[2];
@@ -213,7 +222,7 @@ int fc1_dgrad(const sml_step_args *a, const StepWs &w, cudaStream_t st) {
     if (sml_use_tensor_cores()) {
         SmlPkProb p[2];
         pk_pair(p, r, w.dZpk, 16, SML_PK_OFF_P4, 320, a->theta, 0, nullptr, w.dA, 320, nullptr, w.theta_pk);
-        return sml_launch_umma_packed(p, 2, SML_PK_D1, st, step_ksplit(r));
+        return sml_launch_umma_packed(p, 2, SML_PK_D1, st, step_ksplit(r, 1));
     }
     const float *tu = a->theta, *ti = a->theta + SML_NET_STRIDE;
     SmlGemmProb d1[2] = {
@@ -223,31 +232,40 @@ int fc1_dgrad(const sml_step_args *a, const StepWs &w, cudaStream_t st) {
 }
 
 // fc1/fc2 weight + bias gradients accumulated into g_theta  (theta grads of conv_transfer.py:47-49)
-int fc_wgrads(const sml_step_args *a, const StepWs &w, float *g_theta, cudaStream_t st) {
+// the reduction runs over the batch rows (K = B or 2B): slice it so the few output tiles (4 for dW2,
+// 20 for dW1 per net) spread over the SMs; slices combine with fp32 atomics
+int wgrad_ksplit(int64_t B) { return B >= 2048 ? 16 : (B >= 128 ? 8 : 1); }
+
+int fc2_wgrad(const sml_step_args *a, const StepWs &w, float *g_theta, cudaStream_t st) {
     const Rows r = rows_of(a->batch);
     const int64_t B = r.B, Bp = r.Bp;
     float *gu = g_theta, *gi = g_theta + SML_NET_STRIDE;
-    int rc;
-    // the reduction runs over the batch rows (K = B or 2B): slice it so the few output tiles (4 for dW2,
-    // 20 for dW1 per net) spread over the SMs; slices combine with fp32 atomics
-    const int ksplit = B >= 2048 ? 16 : (B >= 128 ? 8 : 1);
     if (sml_use_tensor_cores()) {
         // tensor-core tiles are 128 rows tall: compute dW2^T [512, 64] = g(Z1)^T dY and store it transposed
         SmlGemmProb w2t[2] = {
             {w.Z1, w.dY, nullptr, nullptr, gu + SML_OFF_F2W, 512, 64, (int)B, 512, 64, 512},
             {w.Z1 + Bp * 512, w.dY + Bp * 64, nullptr, nullptr, gi + SML_OFF_F2W, 512, 64, (int)(2 * B), 512, 64, 512}};
-        rc = sml_launch_umma_gemm(w2t, 2, SML_A_KM_GELU, SML_B_KN, SML_EPI_ACCUM, 1, 64, st, ksplit);
-    } else {
-        SmlGemmProb w2[2] = {
-            {w.dY, w.Z1, nullptr, nullptr, gu + SML_OFF_F2W, 64, 512, (int)B, 64, 512, 512},
-            {w.dY + Bp * 64, w.Z1 + Bp * 512, nullptr, nullptr, gi + SML_OFF_F2W, 64, 512, (int)(2 * B), 64, 512, 512}};
-        rc = sml_launch_sgemm(w2, 2, SML_A_KM, SML_B_KN_GELU, SML_EPI_ACCUM, st);
+        return sml_launch_umma_gemm(w2t, 2, SML_A_KM_GELU, SML_B_KN, SML_EPI_ACCUM, 1, 64, st,
+                                    sml_debug_ksplit(2) > 0 ? sml_debug_ksplit(2) : wgrad_ksplit(B));
     }
-    if (rc) return rc;
+    SmlGemmProb w2[2] = {
+        {w.dY, w.Z1, nullptr, nullptr, gu + SML_OFF_F2W, 64, 512, (int)B, 64, 512, 512},
+        {w.dY + Bp * 64, w.Z1 + Bp * 512, nullptr, nullptr, gi + SML_OFF_F2W, 64, 512, (int)(2 * B), 64, 512, 512}};
+    return sml_launch_sgemm(w2, 2, SML_A_KM, SML_B_KN_GELU, SML_EPI_ACCUM, st);
+}
+
+int fc1_wgrad(const sml_step_args *a, const StepWs &w, float *g_theta, cudaStream_t st) {
+    const Rows r = rows_of(a->batch);
+    const int64_t B = r.B, Bp = r.Bp;
+    float *gu = g_theta, *gi = g_theta + SML_NET_STRIDE;
+    const int ksplit = wgrad_ksplit(B);
+    int rc;
     SmlGemmProb w1[2] = {
         {w.dZ1, w.A, nullptr, nullptr, gu + SML_OFF_F1W, 512, 320, (int)B, 512, 320, 320},
         {w.dZ1 + Bp * 512, w.A + Bp * 320, nullptr, nullptr, gi + SML_OFF_F1W, 512, 320, (int)(2 * B), 512, 320, 320}};
-    if (sml_use_tensor_cores()) rc = sml_launch_umma_gemm(w1, 2, SML_A_KM, SML_B_KN, SML_EPI_ACCUM, 0, 64, st, ksplit > 2 ? ksplit / 2 : 1);
+    if (sml_use_tensor_cores())
+        rc = sml_launch_umma_gemm(w1, 2, SML_A_KM, SML_B_KN, SML_EPI_ACCUM, 0, 64, st,
+                                  sml_debug_ksplit(3) > 0 ? sml_debug_ksplit(3) : (ksplit > 2 ? ksplit / 2 : 1));
     else rc = sml_launch_sgemm(w1, 2, SML_A_KM, SML_B_KN, SML_EPI_ACCUM, st);
     if (rc) return rc;
     if (sml_use_tensor_cores()) return SML_OK;     // bias gradients already accumulated by k_loss and the d2 epilogue
@@ -256,6 +274,12 @@ int fc_wgrads(const sml_step_args *a, const StepWs &w, float *g_theta, cudaStrea
                            {w.dZ1, gu + SML_OFF_F1B, (int)B, 512, 512},
                            {w.dZ1 + Bp * 512, gi + SML_OFF_F1B, (int)(2 * B), 512, 512}};
     return sml_launch_colsum(cs, 4, st);
+}
+
+int fc_wgrads(const sml_step_args *a, const StepWs &w, float *g_theta, cudaStream_t st) {
+    int rc = fc2_wgrad(a, w, g_theta, st);
+    if (rc) return rc;
+    return fc1_wgrad(a, w, g_theta, st);
 }
 
 int mf_step_impl(const sml_step_args *a, bool pack_theta, void *stream) {
@@ -273,13 +297,18 @@ int mf_step_impl(const sml_step_args *a, bool pack_theta, void *stream) {
     }
     rc = forward_and_loss(a, w, true, false, pack_theta, (float)a->l2, nullptr, st);
     if (rc) return rc;
-    rc = fc1_dgrad(a, w, st);
-    if (rc) return rc;
-    SmlRowGroup g[3];
-    make_groups(a, g);
-    SmlConvBwdGroup bg[3] = {{g[0], a->g_user, nullptr}, {g[1], a->g_item, nullptr}, {g[2], a->g_item, nullptr}};
-    rc = sml_launch_conv_bwd(bg, 3, a->variant, w.dA, (float)a->l2, nullptr, st);
-    if (rc) return rc;
+    const int dbg = sml_debug_mask();                  // profiling aid (sml_debug_set_mask): 0 in production
+    if (dbg & (4 | 8 | 128 | 256)) return SML_OK;
+    if (!(dbg & 2)) {
+        rc = fc1_dgrad(a, w, st);
+        if (rc) return rc;
+        SmlRowGroup g[3];
+        make_groups(a, g);
+        SmlConvBwdGroup bg[3] = {{g[0], a->g_user, nullptr}, {g[1], a->g_item, nullptr}, {g[2], a->g_item, nullptr}};
+        rc = sml_launch_conv_bwd(bg, 3, a->variant, w.dA, (float)a->l2, nullptr, st);
+        if (rc) return rc;
+    }
+    if (dbg & 64) return SML_OK;
     if (lazy) return sml_launch_adam_rows(ar, 3, a->adam_state, 1, 0.9, 0.999, 1e-8, st);   // this step, on the touched rows
     // dense Adam on both latent tables, weight_decay = 0 (model/transfer.py:392); also re-zeroes the gradients
     rc = sml_adam_dense(a->hat_user, a->m_user, a->v_user, a->g_user, a->n_users * SML_D, a->adam_state, 0.9, 0.999, 1e-8, 0.0, 1, stream);
@@ -393,24 +422,31 @@ int sml_tr_step(const sml_step_args *a, void *stream) {
     SML_REQUIRE(a->g_theta && a->m_theta && a->v_theta && a->adam_state, SML_E_BADARG, "sml_tr_step: null theta-gradient / Adam-state pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const StepWs w = carve(a->workspace, a->batch);
-    rc = forward_and_loss(a, w, false, true, true, 0.f, nullptr, st, a->g_theta, a->adam_state, a->lr);   // theta changes every step: re-pack
-    if (rc) return rc;
     SideStream *ss = side_stream();
     SML_REQUIRE(ss, SML_E_CUDA, "sml_tr_step: could not create the side stream");
-    SML_CUDA_OK(cudaEventRecord(ss->fork, st));
-    SML_CUDA_OK(cudaStreamWaitEvent(ss->s, ss->fork, 0));
-    rc = fc_wgrads(a, w, a->g_theta, ss->s);                               // branch 1: dW2, dW1 (+ bias sums on the SIMT path)
+    rc = forward_and_loss(a, w, false, true, true, 0.f, nullptr, st, a->g_theta, a->adam_state, a->lr);   // theta changes every step: re-pack
     if (rc) return rc;
-    SML_CUDA_OK(cudaEventRecord(ss->join, ss->s));
-    rc = fc1_dgrad(a, w, st);                                              // branch 2: dA, conv backward
-    if (rc) return rc;
-    SmlRowGroup g[3];
-    make_groups(a, g);
-    float *gu = a->g_theta, *gi = a->g_theta + SML_NET_STRIDE;
-    SmlConvBwdGroup bg[3] = {{g[0], nullptr, gu}, {g[1], nullptr, gi}, {g[2], nullptr, gi}};
-    rc = sml_launch_conv_bwd(bg, 3, a->variant, w.dA, 0.f, nullptr, st);
-    if (rc) return rc;
-    SML_CUDA_OK(cudaStreamWaitEvent(st, ss->join, 0));
+    const int dbg = sml_debug_mask();
+    if (dbg & (4 | 8 | 128 | 256)) return SML_OK;
+    if (!(dbg & 1)) {
+        SML_CUDA_OK(cudaEventRecord(ss->fork, st));
+        SML_CUDA_OK(cudaStreamWaitEvent(ss->s, ss->fork, 0));
+        rc = fc_wgrads(a, w, a->g_theta, ss->s);                           // branch 1: dW2, dW1 (+ bias sums on the SIMT path)
+        if (rc) return rc;
+        SML_CUDA_OK(cudaEventRecord(ss->join, ss->s));
+    }
+    if (!(dbg & 2)) {
+        rc = fc1_dgrad(a, w, st);                                          // branch 2: dA, conv backward
+        if (rc) return rc;
+        SmlRowGroup g[3];
+        make_groups(a, g);
+        float *gu = a->g_theta, *gi = a->g_theta + SML_NET_STRIDE;
+        SmlConvBwdGroup bg[3] = {{g[0], nullptr, gu}, {g[1], nullptr, gi}, {g[2], nullptr, gi}};
+        rc = sml_launch_conv_bwd(bg, 3, a->variant, w.dA, 0.f, nullptr, st);
+        if (rc) return rc;
+    }
+    if (!(dbg & 1)) SML_CUDA_OK(cudaStreamWaitEvent(st, ss->join, 0));
+    if (dbg & 64) return SML_OK;
     // Adam with coupled L2 (weight_decay = TR_l2, model/transfer.py:393) over the whole theta block
     return sml_adam_dense(a->theta, a->m_theta, a->v_theta, a->g_theta, 2 * (int64_t)SML_NET_STRIDE, a->adam_state, 0.9, 0.999,
                           1e-8, a->l2, 1, stream);

@@ -89,9 +89,13 @@ template <int BN> struct PkSmem {
     static constexpr uint32_t TOTAL = PKG_STAGES * STAGE + 64;
 };
 
-template <int BN, int EPI>
+// BROWS = rows per block of the packed B operand in memory.  BROWS == BN: one bulk copy per block.  BROWS = 128 with BN = 64
+// (small batches: twice the CTAs, each pulling less through its SM's L2 port and running half the epilogue): the 64 rows
+// of a tile are 8 consecutive 8-row groups inside the hi half and inside the lo half of a 128-row block, i.e. two copies.
+template <int BN, int EPI, int BROWS = BN>
 __global__ void __launch_bounds__(PKG_THREADS, 1)
 k_umma_packed(PkParams P) {
+    static_assert(BROWS == BN || (BROWS == 128 && BN == 64), "unsupported packed-B block shape");
     extern __shared__ __align__(128) uint8_t smem[];
     using S = PkSmem<BN>;
     // split-K: blockIdx.z = problem * ksplit + slice.  A single CTA streaming K = 512 pulls 0.6 MB through one SM's
@@ -131,14 +135,20 @@ k_umma_packed(PkParams P) {
     if (warp == 0) {
         if (lane == 0) {
             const uint8_t *a = p.A + (size_t)(p.a_tile0 + tile_m) * KC * S::A_BYTES;
-            const uint8_t *b = p.B + (size_t)tile_n * KC * S::B_BYTES;
+            constexpr uint32_t B_SRC = pk_block_bytes(BROWS);
+            const uint8_t *b = p.B + (size_t)(tile_n * BN / BROWS) * KC * B_SRC + (size_t)((tile_n * BN) % BROWS / 8) * PK_SBO;
             for (int c = c_beg; c < c_end; ++c) {
                 const int i = c - c_beg, s = i % PKG_STAGES;
                 if (i >= PKG_STAGES) mbar_wait(&empty[s], ((i / PKG_STAGES) - 1) & 1);
                 uint8_t *st = smem + s * S::STAGE;
                 mbar_expect_tx(&full[s], S::STAGE);
                 bulk_g2s(st, a + (size_t)c * S::A_BYTES, S::A_BYTES, &full[s]);
-                bulk_g2s(st + S::A_BYTES, b + (size_t)c * S::B_BYTES, S::B_BYTES, &full[s]);
+                if (BROWS == BN) {
+                    bulk_g2s(st + S::A_BYTES, b + (size_t)c * B_SRC, S::B_BYTES, &full[s]);
+                } else {
+                    bulk_g2s(st + S::A_BYTES, b + (size_t)c * B_SRC, pk_half_bytes(BN), &full[s]);
+                    bulk_g2s(st + S::A_BYTES + pk_half_bytes(BN), b + (size_t)c * B_SRC + pk_half_bytes(BROWS), pk_half_bytes(BN), &full[s]);
+                }
             }
         }
     } else if (warp == 1) {
@@ -301,9 +311,9 @@ __global__ void __launch_bounds__(256) k_pack_theta(const float *__restrict__ th
     }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int BROWS = BN>
 int launch_pk(const PkParams &P, dim3 grid, cudaStream_t st) {
-    auto kern = k_umma_packed<BN, EPI>;
+    auto kern = k_umma_packed<BN, EPI, BROWS>;
     static bool attr_set = false;
     if (!attr_set) {
         SML_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PkSmem<BN>::TOTAL));
@@ -330,10 +340,21 @@ int sml_launch_umma_packed(const SmlPkProb *probs, int n_probs, int epi, cudaStr
         SML_REQUIRE(probs[i].N == N && probs[i].KC >= 1, SML_E_BADARG, "packed gemm: grouped problems must share N and have KC >= 1");
     }
     if (max_mt == 0) return SML_OK;
+    // few row tiles (the B = 256 transfer step has 6): 128 x 64 tiles double the CTAs of the N = 512 GEMMs (24 -> 48), each
+    // pulls 25 % less through its SM's L2 port and runs half the epilogue.  sml_debug_set_mask(512) keeps the wide tiles.
+    int tot_mt = 0;
+    for (int i = 0; i < n_probs; ++i) tot_mt += probs[i].m_tiles;
+    const bool narrow = tot_mt <= 12 && !(sml_debug_mask() & 512);
     switch (epi) {
-        case SML_PK_FC1: SML_REQUIRE(N % 128 == 0, SML_E_BADARG, "packed gemm: fc1 N"); return launch_pk<128, SML_PK_FC1>(P, dim3(N / 128, max_mt, n_probs), st);
+        case SML_PK_FC1:
+            SML_REQUIRE(N % 128 == 0, SML_E_BADARG, "packed gemm: fc1 N");
+            if (narrow) return launch_pk<64, SML_PK_FC1, 128>(P, dim3(N / 64, max_mt, n_probs), st);
+            return launch_pk<128, SML_PK_FC1>(P, dim3(N / 128, max_mt, n_probs), st);
         case SML_PK_FC2: SML_REQUIRE(N % 64 == 0, SML_E_BADARG, "packed gemm: fc2 N"); return launch_pk<64, SML_PK_FC2>(P, dim3(N / 64, max_mt, n_probs * ksplit), st);
-        case SML_PK_D2: SML_REQUIRE(N % 128 == 0, SML_E_BADARG, "packed gemm: d2 N"); return launch_pk<128, SML_PK_D2>(P, dim3(N / 128, max_mt, n_probs), st);
+        case SML_PK_D2:
+            SML_REQUIRE(N % 128 == 0, SML_E_BADARG, "packed gemm: d2 N");
+            if (narrow) return launch_pk<64, SML_PK_D2, 128>(P, dim3(N / 64, max_mt, n_probs), st);
+            return launch_pk<128, SML_PK_D2>(P, dim3(N / 128, max_mt, n_probs), st);
         case SML_PK_D1: SML_REQUIRE(N % 64 == 0, SML_E_BADARG, "packed gemm: d1 N"); return launch_pk<64, SML_PK_D1>(P, dim3(N / 64, max_mt, n_probs * ksplit), st);
     }
     sml_set_error("packed gemm: bad epilogue %d", epi);

@@ -85,6 +85,9 @@ def test_sharded_epoch_api_matches_step_api():
         s.flush()
         res.append((s.user.clone(), s.item.clone(), s.transfer.theta.clone(), float(lm), float(lt)))
     a, b = res
-    assert (a[0] - b[0]).abs().max().item() < 2e-6 and (a[1] - b[1]).abs().max().item() < 2e-6
-    assert (a[2] - b[2]).abs().max().item() < 1e-5
-    assert abs(a[3] - b[3]) < 1e-4 * abs(a[3]) and abs(a[4] - b[4]) < 1e-4 * abs(a[4])
+    du, di, dt = ((a[k] - b[k]).abs().max().item() for k in range(3))
+    # same kernels, same inputs: the two runs differ only through the order of fp32 atomics (row-gradient scatter, split-K
+    # slices, theta-gradient reductions); Adam turns a relative gradient noise of 1e-6 into up to ~lr * 1e-2 on theta
+    assert du < 2e-6 and di < 2e-6, (du, di)
+    assert dt < 1e-4, dt
+    assert abs(a[3] - b[3]) < 1e-4 * abs(a[3]) and abs(a[4] - b[4]) < 1e-4 * abs(a[4]), (a[3], b[3], a[4], b[4])
