@@ -138,6 +138,8 @@ def cpu_port_periods_per_s(shape, seed=0, scale=1.0, verbose=False, device="cpu"
     ids = lambda B: (rng.integers(0, U, B), rng.integers(0, I, B), rng.integers(0, I, B))
     rows = np.concatenate([rng.integers(0, U, (n_ev, 1)), rng.integers(0, I, (n_ev, 1000))], 1)
     p.mf_step(*ids(Bm)); p.tr_step(*ids(Bt)); sync()              # warm-up (allocator, thread pool)
+    if gpu:                                                       # cuDNN algorithm choice / allocator growth of the two big calls
+        p.updata(max_rows=n_up); p.test_model(rows, HYPER["topK"]); sync()
     t = time.perf_counter()
     for _ in range(n_mf):
         p.mf_step(*ids(Bm))

@@ -41,24 +41,26 @@ def main():
             tr = ConvTransfer_com(64, 64).to(dev)
     lu, li, hu, hi = T(U, 64), T(I, 64), T(U, 64), T(I, 64)
     z = lambda t: torch.zeros_like(t)
-    for B, kind in ((1024, "mf"), (256, "tr"), (248, "mf"), (8192, "mf"), (8192, "tr")):
+    for B, kind in ((1024, "mf"), (1024, "mfl"), (256, "tr"), (248, "mf"), (8192, "mf"), (8192, "mfl"), (8192, "tr")):
         if PROFILE and "%s%d" % (kind, B) not in PROFILE.split(","):
             continue
         u = torch.randint(0, U, (B,), generator=g).to(dev); i = torch.randint(0, I, (B,), generator=g).to(dev)
         j = torch.randint(0, I, (B,), generator=g).to(dev)
         loss = torch.zeros(2, device=dev)
         ws = torch.zeros(int(ops.lib().sml_step_workspace_bytes(B)), dtype=torch.uint8, device=dev)
-        if kind == "mf":
+        if kind in ("mf", "mfl"):      # mf: dense Adam sweep; mfl: row-lazy exact Adam (meta_train's default), same ids every step
+            st = ops.new_adam_state(dev, history=kind == "mfl")
+            stamps = dict(stamp_user=ops.new_row_stamps(U, st), stamp_item=ops.new_row_stamps(I, st)) if kind == "mfl" else {}
             a = ops.make_step_args(user=u, item=i, neg=j, last_user=lu, last_item=li, hat_user=hu, hat_item=hi, theta=tr.theta,
-                                   adam_state=ops.new_adam_state(dev), lr=1e-4, l2=1e-6, loss_out=loss, workspace=ws,
-                                   g_user=z(hu), g_item=z(hi), m_user=z(hu), v_user=z(hu), m_item=z(hi), v_item=z(hi))
-            us = timed_graph(lambda: ops.mf_step(a), 10)
+                                   adam_state=st, lr=1e-4, l2=1e-6, loss_out=loss, workspace=ws,
+                                   g_user=z(hu), g_item=z(hi), m_user=z(hu), v_user=z(hu), m_item=z(hi), v_item=z(hi), **stamps)
+            us = timed_graph(lambda: ops.mf_step(a, flush=False), 10)
         else:
             a = ops.make_step_args(user=u, item=i, neg=j, last_user=lu, last_item=li, hat_user=hu, hat_item=hi, theta=tr.theta,
                                    adam_state=ops.new_adam_state(dev), lr=1e-5, l2=1e-4, loss_out=loss, workspace=ws,
                                    g_theta=tr.theta_grad, m_theta=z(tr.theta), v_theta=z(tr.theta))
             us = timed_graph(lambda: ops.tr_step(a), 10)
-        print("%s step  B=%5d : %8.1f us   (%.2f M triples/s)" % (kind, B, us, B / us))
+        print("%-3s step  B=%5d : %8.1f us   (%.2f M triples/s)" % (kind, B, us, B / us))
     out = torch.empty_like(hu)
     us = timed_graph(lambda: ops.transfer_forward(lu, hu, tr.theta[:ops.NET_STRIDE], out=out), 3)
     print("transfer_forward %d rows: %8.1f us  (%.1f TFLOP/s fp32-equiv, %.0f M rows/s)" % (U, us, U * 403456 / us / 1e6, U / us))
