@@ -40,6 +40,7 @@ EVAL_BYTES_PER_ROW = (1 + 1000) * 256 + 1001 * 8          # 264 26
 TRANSFER_FLOP_PER_ROW = 403456
 TRANSFER_BYTES_PER_ROW = 768
 EVAL_NCU_DRAM_BYTES = 655_940_000                          # dram__bytes_read.sum + dram__bytes_write.sum of one 75 000-row launch (ncu --set full, r01)
+EVAL_NCU_DRAM_BYTES_PREFILTER = None                       # same for k_eval_prefilter (filled from profiles/r01_kernels_ncu.md when captured)
 
 
 def make_args(**over):
@@ -401,11 +402,16 @@ def run_ours(a):
         "phase_counts_per_period": {k: v[0] / K for k, v in phases.items()},
         "kernels": kern,
         "roofline_phases": roofline_phases,
-        "roofline": {"kernel": "k_eval_candidates", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": ach / hbm_peak, "traffic": EVAL_NCU_DRAM_BYTES if shape["rows"] == 75000 else None, "peak_source": peak_src,
-                     "note": "algorithmic bytes = 264264 B x rows per launch (19.8 GB); the 31 MB item table is L2 resident "
-                             "(ncu: L2 hit 95%, DRAM traffic 0.66 GB per launch = the 600 MB id file + tables, profiles/r01_kernels_ncu.md), "
-                             "so frac exceeds 1: the kernel runs at the L2->SM limit (~6300 B/clk x 1.965 GHz = 12.4 TB/s)"},
+        "roofline": {"kernel": "k_eval_prefilter" if ops.EVAL_PREFILTER else "k_eval_candidates", "bound": "hbm", "achieved": ach,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                     "traffic": ((EVAL_NCU_DRAM_BYTES_PREFILTER if ops.EVAL_PREFILTER else EVAL_NCU_DRAM_BYTES)
+                                 if shape["rows"] == 75000 else None),
+                     "peak_source": peak_src,
+                     "note": "algorithmic bytes = 264264 B x rows per launch (19.8 GB, SURVEY 8d: fp32 rows); the 31 MB item table is L2 "
+                             "resident (ncu: L2 hit 95%, DRAM traffic 0.66 GB per launch = the 600 MB id file + tables, "
+                             "profiles/r01_kernels_ncu.md), so frac exceeds 1.  The fp32 kernel runs at the L2->SM limit (~6300 B/clk x "
+                             "1.965 GHz = 12.4 TB/s); k_eval_prefilter gets the identical counts from a bf16 copy of the table (128 B per "
+                             "candidate) + exact fp32 re-scoring of the ~0.6 % it cannot decide, i.e. it reads about half of those bytes"},
     }
     if rank == 0:
         if world == 1 and not a.no_cpu_baseline:

@@ -93,6 +93,15 @@ uint64_t sml_launch_count(void);
  * row_stride = number of int64 per row (>= 1 + C). */
 int sml_eval_candidates(const float *user_tab, const float *item_tab, int d, const int64_t *rows, int64_t n_rows,
                         int64_t row_stride, int n_cand, int32_t *gt, int32_t *eq, void *stream);
+/* The same counts, bit for bit, from about half the bytes: candidates are first compared through a bf16 copy of the item
+ * table (built into item_bf16, sml_eval_prefilter_bytes(n_items) bytes of caller scratch, on every call) with a rigorous
+ * error bound; only the undecided few are re-scored in fp32 with the operation order of sml_eval_candidates.
+ * Measured on B200 (profiles/r01_kernels_ncu.md): L2 sectors halve, instruction issue becomes the limit, same run time --
+ * kept as an option, the fp32 kernel stays the default. */
+size_t sml_eval_prefilter_bytes(int64_t n_items);
+int sml_eval_candidates_prefilter(const float *user_tab, const float *item_tab, int64_t n_items, int d, void *item_bf16,
+                                  const int64_t *rows, int64_t n_rows, int64_t row_stride, int n_cand, int32_t *gt, int32_t *eq,
+                                  void *stream);
 /* Per batch of `batch` consecutive test rows (evaluation2.test_model batches of 1024,
  * evalution/evaluation2.py:8-26): hits[b] = #{rank < topk}, ndcg[b] = sum 1/log2(rank+2)
  * over hits (fp32, fixed summation order), rank = gt + (tie_loses ? eq : 0). */

@@ -44,6 +44,8 @@ _PROTOS = {
     "sml_sm_count": (_i32, []),
     "sml_launch_count": (C.c_uint64, []),
     "sml_eval_candidates": (_i32, [_vp, _vp, _i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp]),
+    "sml_eval_prefilter_bytes": (_sz, [_i64]),
+    "sml_eval_candidates_prefilter": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp]),
     "sml_eval_reduce": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),
     "sml_pair_scores": (_i32, [_vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _vp]),
     "sml_transfer_fwd_workspace_bytes": (_sz, [_i64]),

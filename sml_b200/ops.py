@@ -6,6 +6,7 @@ nothing falls back to PyTorch operators: a missing library or a failing call rai
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -28,12 +29,24 @@ def _i64(t, name):
 
 
 # ------------------------------------------------------------------ evaluation
-def eval_candidates(user_tab, item_tab, rows):
-    """rows: int64 [n, 1+C] (user, positive, negatives...) -> (gt int32[n], eq int32[n])."""
+EVAL_PREFILTER = os.environ.get("SML_EVAL_PREFILTER", "0") == "1"
+
+
+def eval_candidates(user_tab, item_tab, rows, prefilter=None):
+    """rows: int64 [n, 1+C] (user, positive, negatives...) -> (gt int32[n], eq int32[n]).
+    ``prefilter`` (default off, SML_EVAL_PREFILTER=1 turns it on): bf16 pre-filter with exact fp32 fallback -- identical
+    counts from about half the L2 bytes (sml_eval_candidates_prefilter), but measured no faster: it trades the L1/L2 limit of
+    the fp32 kernel for an instruction-issue limit (profiles/r01_kernels_ncu.md)."""
     _f32(user_tab, "user_tab"); _f32(item_tab, "item_tab"); _i64(rows, "rows")
     n, w = rows.shape
     gt = torch.empty(n, dtype=torch.int32, device=rows.device)
     eq = torch.empty(n, dtype=torch.int32, device=rows.device)
+    if EVAL_PREFILTER if prefilter is None else prefilter:
+        scratch = _workspace(lib().sml_eval_prefilter_bytes(item_tab.shape[0]), rows.device, "eval_bf16")
+        check(lib().sml_eval_candidates_prefilter(ptr(user_tab), ptr(item_tab), item_tab.shape[0], user_tab.shape[1], ptr(scratch),
+                                                  ptr(rows), n, rows.stride(0), w - 1, ptr(gt), ptr(eq), stream()),
+              "eval_candidates_prefilter")
+        return gt, eq
     check(lib().sml_eval_candidates(ptr(user_tab), ptr(item_tab), user_tab.shape[1], ptr(rows), n, rows.stride(0), w - 1,
                                     ptr(gt), ptr(eq), stream()), "eval_candidates")
     return gt, eq

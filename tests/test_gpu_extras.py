@@ -148,3 +148,41 @@ def test_mf_epoch_row_lazy_adam_matches_dense():
     for x, y in zip(d[:4], l[:4]):
         assert (x - y).abs().max().item() < 2e-6
     assert abs(float(d[4][1] - l[4][1])) < 1e-4 * abs(float(d[4][1]))
+
+
+def test_eval_prefilter_counts_equal_the_exact_kernel():
+    """sml_eval_candidates_prefilter (bf16 estimate + error bound + exact fp32 fallback) must return the same gt / eq as
+    sml_eval_candidates for every input: random scores, exact ties, near-ties far inside the bf16 error, NaN / Inf / zero rows,
+    huge and tiny magnitudes, ragged candidate counts."""
+    from sml_b200 import ops
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(9)
+    U, I = 700, 5000
+    ut = torch.randn(U, 64, generator=gen)
+    it = torch.randn(I, 64, generator=gen)
+    # adversarial item rows
+    it[10] = it[11]                                   # exact duplicate -> exact ties when both are candidates
+    it[12] = it[11] * (1 + 1e-7)                      # differs in the last fp32 bits only
+    it[13] = it[11] + 1e-6 * torch.randn(64, generator=gen)
+    it[14] = float("nan"); it[15, 3] = float("inf"); it[16, 5] = -float("inf"); it[17] = 0.0; it[18] = -0.0
+    it[19] = 3e37; it[20] = 1e-38; it[21] = 1e-42     # overflow to inf in bf16 / fp32 denormals
+    it[22:40] = it[11] + 3e-4 * torch.randn(18, 64, generator=gen)   # inside the bf16 error band of row 11
+    ut[5] = 0.0; ut[6] = float("nan"); ut[7, 2] = float("inf"); ut[8] = 1e-30; ut[9] = 1e18
+    ut, it = ut.to(dev), it.to(dev)
+    for C in (1000, 37, 1):
+        n = 900
+        rows = torch.empty(n, 1 + C, dtype=torch.int64)
+        rows[:, 0] = torch.randint(0, U, (n,), generator=gen)
+        rows[:, 1:] = torch.randint(0, I, (n, C), generator=gen)
+        rows[:200, 0] = torch.randint(0, 12, (200,), generator=gen)            # the special user rows
+        rows[:, 1][::3] = 11                                                   # positive = the row with look-alikes
+        if C > 30:
+            rows[:, 2:32] = torch.randint(10, 40, (n, 30), generator=gen)     # candidates from the adversarial block
+        rows = rows.to(dev)
+        g0, e0 = ops.eval_candidates(ut, it, rows, prefilter=False)
+        g1, e1 = ops.eval_candidates(ut, it, rows, prefilter=True)
+        assert torch.equal(g0, g1) and torch.equal(e0, e1), C
+        assert int(e0.sum()) > 0 or C == 1
+    # an empty file
+    z = ops.eval_candidates(ut, it, torch.empty(0, 1001, dtype=torch.int64, device=dev), prefilter=True)
+    assert z[0].numel() == 0
