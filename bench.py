@@ -180,8 +180,11 @@ def run_reference_arm(a):
     out = {"impl": "reference", "metric": "periods/sec", "value": v, "unit": "periods/s", "n_gpus": a.gpus, "steps": a.steps,
            "warmup": a.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "configs[1]: Yelp-shaped SML period (U=59082, I=122816, 75000 rows, multi_num=10, ConvTransfer_com), CPU port",
-                      "note": "each step is a bounded sample composed to one period"},
+           "config": {"workload": "configs[1]: Yelp-shaped SML period stream, ConvTransfer_com, one period per step",
+                      "n_users": YELP["n_users"], "n_items": YELP["n_items"], "rows_per_period": YELP["rows"],
+                      "candidates_per_eval_row": 1000, **HYPER,
+                      "note": "the reference's operator sequence (oracle/torch_port.py, stock CPU PyTorch, all host threads); each step "
+                              "times a bounded sample of the period's four phases and composes it to one period"},
            "cpu_baseline": {"value": v, "unit": "periods/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": v, "unit": "periods/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
