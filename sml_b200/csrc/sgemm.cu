@@ -1,9 +1,8 @@
-// Grouped fp32 SIMT GEMM used by the step kernels for the small-batch fc1/fc2 forward,
-// data-gradient and weight-gradient products (B = 1024 / 256 triples => 3072 / 768 rows,
-// model/transfer.py:463-511,701-728), and a column-sum kernel for the bias gradients.
-// Exact fp32 FFMA accumulation (no TF32 rounding), so results are directly comparable with the
-// reference's fp32 cuBLAS/CPU path.  The large-N transfer forward (updata) has its own
-// tensor-core kernel (umma_transfer.cu); this kernel is the latency-oriented companion.
+// Grouped fp32 SIMT GEMM: the A/B reference of the tensor-core path (SML_GEMM=simt selects it for every fc1 / fc2 forward,
+// data-gradient and weight-gradient product of the steps and of the full-table transfer, model/transfer.py:463-511,701-728,
+// 884-902), and a column-sum kernel for the bias gradients of that path.  Exact fp32 FFMA accumulation (no TF32 rounding),
+// so results are directly comparable with the reference's fp32 cuBLAS/CPU path.  The default path is umma_packed.cu /
+// umma_gemm.cu (tcgen05, 3xTF32).
 //
 // C[M,N] = epi( sum_k opA(A)[m,k] * opB(B)[k,n] ), 64x64x16 tiles, 256 threads, 4x4 per thread.
 #include "sml_common.cuh"

@@ -115,11 +115,10 @@ void pk_pair(SmlPkProb out[2], const Rows &r, const uint8_t *A, int KC, size_t w
     }
 }
 
-// forward through fc2 + loss + data gradients down to dZ1 (shared by all step flavours).
-// need_plain_A: the transfer step's fc1 weight gradient reads A.
 // Fork / join helper: the two weight-gradient GEMMs of the transfer step only feed the final Adam update, so they run
-// on a library-owned side stream concurrently with dA = dZ1 W1 and the conv backward (both ~25 us at B = 256).  Event
-// record / wait are stream-capturable, so inside a CUDA graph this becomes two parallel branches.
+// on a library-owned side stream concurrently with dA = dZ1 W1 and the conv backward (21 vs 18 us at B = 256,
+// profiles/r01_tr_step_breakdown.md).  Event record / wait are stream-capturable, so inside a CUDA graph this becomes
+// two parallel branches.
 struct SideStream {
     cudaStream_t s = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, join2 = nullptr;
@@ -139,6 +138,8 @@ SideStream *side_stream() {
     return &x;
 }
 
+// forward through fc2 + loss + data gradients down to dZ1 (shared by all step flavours).
+// need_plain_A: the transfer step's fc1 weight gradient reads A.
 // g_theta != null (tensor-core path): the fc2 / fc1 bias gradients are accumulated by the loss kernel and by the d2
 // epilogue.  tick_state != null: the Adam tick rides in the theta packer's launch.
 int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, bool need_plain_A, bool pack_theta, float l2,
