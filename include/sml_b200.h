@@ -258,6 +258,17 @@ int64_t sml_host_rejection_walk(const int64_t *draws_host, int64_t n_draws, cons
                                 const int64_t *item_all_host, const int64_t *keys_host, int64_t n_keys, int64_t span,
                                 int64_t *neg_host);
 
+/* The same walk with the membership test through an open-addressing hash set (one or two probes instead of a
+ * 17-level binary search) and resumable, so the caller draws exactly as many numbers as the reference consumes:
+ *   sml_host_keyset_build: table[table_size] (power of two >= 2 n) <- the period's user*span+item keys;
+ *   sml_host_rejection_walk_hashed: continues at sample *sample_io, stops when samples or draws run out, returns the
+ *   draws consumed (called with as many draws as samples remain, it consumes all of them). */
+int sml_host_keyset_build(const int64_t *users_host, const int64_t *items_host, int64_t n, int64_t span, int64_t *table_host,
+                          int64_t table_size);
+int64_t sml_host_rejection_walk_hashed(const int64_t *draws_host, int64_t n_draws, const int64_t *users_host, int64_t n,
+                                       int64_t *sample_io, const int64_t *item_all_host, const int64_t *table_host,
+                                       int64_t table_size, int64_t span, int64_t *neg_host);
+
 /* ---- GEMM building block (exposed for tests and profiling) ---------------------------------
  * C[M,N] = epi(opA(A) opB(B)) with the fc-layer GEMM kernels the steps use.  a_mode: 0 A[m][k], 1 same
  * with GELU applied on load, 2 A[k][m], 3 A[k][m] + GELU.  b_mode: 0 B[n][k], 1 B[k][n], 2 B[k][n] + GELU.

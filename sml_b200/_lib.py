@@ -67,6 +67,8 @@ _PROTOS = {
     "sml_philox_negatives": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, C.c_uint64, C.c_uint64, _vp, _vp]),
     "sml_gather_pairs": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "sml_scatter_grads": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _dbl, _dbl, _vp]),
+    "sml_host_keyset_build": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64]),
+    "sml_host_rejection_walk_hashed": (_i64, [_vp, _i64, _vp, _i64, C.POINTER(_i64), _vp, _vp, _i64, _i64, _vp]),
     "sml_host_rejection_walk": (_i64, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
     "sml_debug_set_mask": (_i32, [_i32]),
     "sml_debug_mask": (_i32, []),

@@ -27,3 +27,54 @@ extern "C" int64_t sml_host_rejection_walk(const int64_t *draws, int64_t n_draws
     }
     return p;                                            // number of draws consumed
 }
+
+// ---- hashed variant ---------------------------------------------------------------------------------
+// The binary search above costs ~17 dependent cache misses per draw (15 ms per 75 000-sample epoch on the host).  The
+// same membership test through an open-addressing hash set of the period's (user * span + item) keys takes one or two
+// probes.  table: int64[table_size], table_size a power of two >= 2 * n, filled here (-1 = empty).
+namespace {
+inline uint64_t mix64(uint64_t x) {
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27; x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return x;
+}
+}  // namespace
+
+extern "C" int sml_host_keyset_build(const int64_t *users, const int64_t *items, int64_t n, int64_t span, int64_t *table,
+                                     int64_t table_size) {
+    if (n < 0 || table_size < 2 || (table_size & (table_size - 1)) != 0 || table_size < 2 * n || (n > 0 && (!users || !items)) || !table)
+        return SML_E_BADARG;
+    const uint64_t mask = (uint64_t)table_size - 1;
+    for (int64_t i = 0; i < table_size; ++i) table[i] = -1;
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t key = users[i] * span + items[i];
+        uint64_t h = mix64((uint64_t)key) & mask;
+        while (table[h] != -1 && table[h] != key) h = (h + 1) & mask;
+        table[h] = key;
+    }
+    return SML_OK;
+}
+
+// Resumable walk: starts at sample *sample_io, stops when the samples or the draws run out, leaves the next sample in
+// *sample_io and returns the number of draws consumed.  Called with exactly as many draws as samples remain it always
+// consumes all of them (every sample needs at least one), so the caller never has to rewind the generator.
+extern "C" int64_t sml_host_rejection_walk_hashed(const int64_t *draws, int64_t n_draws, const int64_t *users, int64_t n,
+                                                  int64_t *sample_io, const int64_t *item_all, const int64_t *table,
+                                                  int64_t table_size, int64_t span, int64_t *neg) {
+    const uint64_t mask = (uint64_t)table_size - 1;
+    int64_t p = 0, s = *sample_io;
+    while (s < n && p < n_draws) {
+        const int64_t it = item_all[draws[p++]];
+        const int64_t key = users[s] * span + it;
+        uint64_t h = mix64((uint64_t)key) & mask;
+        bool hit = false;
+        while (table[h] != -1) {
+            if (table[h] == key) { hit = true; break; }
+            h = (h + 1) & mask;
+        }
+        if (!hit) neg[s++] = it;
+    }
+    *sample_io = s;
+    return p;
+}

@@ -42,39 +42,51 @@ class ReferenceStream(object):
 
     @staticmethod
     def alone_negatives(ds: offlineDataset_withsample, order):
-        """Sequential rejection sampling in sampler order, vectorised between rejections."""
+        """Sequential rejection sampling in sampler order: the draws come from numpy's global generator in exactly the
+        amounts the reference consumes (as many as samples remain, again for the rejected ones, ...), the walk over them
+        is a C helper with a hashed membership test."""
         from .._lib import lib
+        import ctypes as C
         n = len(order)
         users = np.ascontiguousarray(ds.user[order], dtype=np.int64)
         item_all = np.ascontiguousarray(ds.item_all, dtype=np.int64)
-        keys = np.ascontiguousarray(ds._keys, dtype=np.int64)
+        table = ds.key_table()
         P = len(item_all)
-        state = np.random.get_state()
-        margin = max(64, n // 4)
         neg = np.empty(n, dtype=np.int64)
-        walk = lib().sml_host_rejection_walk
-        while True:
-            draws = np.ascontiguousarray(np.random.randint(0, P, size=n + margin), dtype=np.int64)
-            p = walk(draws.ctypes.data, len(draws), users.ctypes.data, n, item_all.ctypes.data, keys.ctypes.data, len(keys),
-                     ds._span, neg.ctypes.data)
-            if p >= 0:
-                break
-            np.random.set_state(state)
-            margin *= 4
-        # leave the global generator exactly where the reference would: p draws consumed
-        np.random.set_state(state)
-        if p:
-            np.random.randint(0, P, size=p)
+        walk = lib().sml_host_rejection_walk_hashed
+        s = C.c_int64(0)
+        while s.value < n:
+            k = n - s.value
+            draws = np.ascontiguousarray(np.random.randint(0, P, size=k), dtype=np.int64)
+            used = walk(draws.ctypes.data, k, users.ctypes.data, n, C.byref(s), item_all.ctypes.data, table.ctypes.data, len(table),
+                        ds._span, neg.ctypes.data)
+            assert used == k                   # every remaining sample needs at least one draw
         return neg.astype(ds.item_all.dtype, copy=False)
+
+
+_UI_CACHE = []      # [(file array, contiguous user column, contiguous item column)], last two period files
+
+
+def _user_item_columns(d):
+    """Contiguous copies of columns 0 and 1 of a period file, made once per file: the per-epoch gathers then hit two
+    600 KB arrays instead of striding through the 600 MB file."""
+    for arr, u, i in _UI_CACHE:
+        if arr is d:
+            return u, i
+    u, i = np.ascontiguousarray(d[:, 0], dtype=np.int64), np.ascontiguousarray(d[:, 1], dtype=np.int64)
+    _UI_CACHE.append((d, u, i))
+    del _UI_CACHE[:-2]
+    return u, i
 
 
 def mf_epoch_triples(ds: trainDataset_withPreSample, order):
     """One MF epoch over a pre-sampled dataset in the given sample order (data/dataset2.py:191-201)."""
     col = ds.current_column()
     d = ds.all_data
-    u, i, j = d[order, 0], d[order, 1], d[order, col]
+    u_all, i_all = _user_item_columns(d)
+    u, i, j = u_all[order], i_all[order], d[order, col]
     ds.advance_epoch()
-    return np.ascontiguousarray(u, dtype=np.int64), np.ascontiguousarray(i, dtype=np.int64), np.ascontiguousarray(j, dtype=np.int64)
+    return u, i, np.ascontiguousarray(j, dtype=np.int64)
 
 
 def tr_epoch_triples(ds: offlineDataset_withsample, order):

@@ -115,6 +115,7 @@ def test_alone_sampler_vectorised_equals_sequential():
     order = rng.permutation(300)
     np.random.seed(9)
     ds = offlineDataset_withsample(data)
+    assert np.array_equal(ds.item_all, np.unique(data[:, 1])) and ds.item_all.dtype == data.dtype
     seq = np.array([ds[i][2] for i in order])
     state_after_seq = np.random.get_state()[1].copy()
     np.random.seed(9)
