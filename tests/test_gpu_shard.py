@@ -87,7 +87,9 @@ def test_sharded_epoch_api_matches_step_api():
     a, b = res
     du, di, dt = ((a[k] - b[k]).abs().max().item() for k in range(3))
     # same kernels, same inputs: the two runs differ only through the order of fp32 atomics (row-gradient scatter, split-K
-    # slices, theta-gradient reductions); Adam turns a relative gradient noise of 1e-6 into up to ~lr * 1e-2 on theta
-    assert du < 2e-6 and di < 2e-6, (du, di)
+    # slices, theta-gradient reductions).  Adam amplifies an absolute gradient noise d on elements with |g| <~ eps = 1e-8 by
+    # lr / eps per step: tables (lr 0.01, d ~ 1e-12) up to ~1e-6 per step, theta (lr 0.001, d ~ 1e-10) up to ~1e-5 per step;
+    # four steps each here
+    assert du < 2e-5 and di < 2e-5, (du, di)
     assert dt < 1e-4, dt
     assert abs(a[3] - b[3]) < 1e-4 * abs(a[3]) and abs(a[4] - b[4]) < 1e-4 * abs(a[4]), (a[3], b[3], a[4], b[4])
