@@ -144,9 +144,10 @@ def test_mf_epoch_row_lazy_adam_matches_dense():
         out.append((hu, hi, z["m_user"], z["v_item"], loss.clone(), int(st[0])))
     d, l = out
     assert d[5] == l[5] == 2 * 10
-    # the gradient scatter uses fp32 atomics (duplicate ids), so the two runs agree to rounding, not bitwise
+    # the gradient scatter and the split-K GEMM slices use fp32 atomics, so the two runs agree to rounding, not bitwise; Adam
+    # turns an absolute gradient noise d (~1e-12 here) on elements with |g| <~ eps into up to lr * d / eps ~ 1e-6 per step
     for x, y in zip(d[:4], l[:4]):
-        assert (x - y).abs().max().item() < 2e-6
+        assert (x - y).abs().max().item() < 2e-5
     assert abs(float(d[4][1] - l[4][1])) < 1e-4 * abs(float(d[4][1]))
 
 
