@@ -55,7 +55,7 @@ def test_checkpoint_resume_is_exact(golden, tmp_path):
     # row-gradient scatter and theta-gradient reductions use fp32 atomics: equal to rounding, not bitwise
     assert (a.MFbase.user_laten.weight.data - b.MFbase.user_laten.weight.data).abs().max().item() < 1e-4
     assert (a.MFbase.item_laten.weight.data - b.MFbase.item_laten.weight.data).abs().max().item() < 1e-4
-    assert (a.transfer.theta - b.transfer.theta).abs().max().item() < 1e-5
+    assert (a.transfer.theta - b.transfer.theta).abs().max().item() < 1e-4
     assert a.MF_optimizer.step_count == b.MF_optimizer.step_count and a.recall == b.recall
 
 
