@@ -132,8 +132,12 @@ class ShardedSML(object):
     """Row-sharded state + the sharded MF step, transfer step, updata and candidate evaluation.
     ``transfer`` is a (replicated) ``ConvTransfer_com``; all tensors live on this rank's GPU."""
 
-    def __init__(self, user_tab, item_tab, transfer, world=1, rank=0, group=None, mf_lr=0.01, l2=1e-6, tr_lr=0.001, tr_l2=1e-4):
-        from . import ops
+    def __init__(self, user_tab, item_tab, transfer, world=1, rank=0, group=None, mf_lr=0.01, l2=1e-6, tr_lr=0.001, tr_l2=1e-4,
+                 ops=None):
+        """``ops``: the local operator module (default: the CUDA library wrappers, sml_b200.ops).  The CPU gloo test injects a
+        numpy stand-in with the same functions to exercise the exchange / lazy-Adam logic without a GPU."""
+        if ops is None:
+            from . import ops
         self.ops = ops
         self.world, self.rank, self.group = world, rank, group
         self.ex = RowExchange(world, rank, group)

@@ -1,0 +1,107 @@
+"""CPU stand-in for the subset of sml_b200.ops that ShardedSML's MF path calls, built on the numpy oracle -- TEST
+INFRASTRUCTURE (tests/test_shard_gloo.py).  It lets the world-size-2 gloo test drive the real exchange plan, the row-lazy
+Adam bookkeeping (tick / catch-up / apply / flush order, stamps, duplicate ids) and the global-batch scaling of
+``ShardedSML`` without a GPU; the arithmetic of each local operator is the oracle's."""
+import numpy as np
+import torch
+
+from oracle import sml_oracle as O
+
+ADAM_HISTORY = 4096
+LOSS_BCE = 0
+VARIANT_COM = 0
+NET_STRIDE = 197344
+
+
+def _np(t):
+    return t.detach().numpy()
+
+
+class _Lib(object):
+    @staticmethod
+    def sml_step_workspace_bytes(B):
+        return 8
+
+
+def lib():
+    return _Lib
+
+
+def step_rows(B):
+    Bp = -(-B // 128) * 128
+    total = Bp + -(-2 * B // 128) * 128
+    return total, Bp, Bp + B
+
+
+def new_adam_state(device, history=False):
+    return torch.zeros(4, dtype=torch.int64)
+
+
+def new_row_stamps(n_rows, state):
+    return torch.full((n_rows,), int(state[0]), dtype=torch.int32)
+
+
+_LR = {}
+
+
+def adam_tick(state, lr, beta1=0.9, beta2=0.999):
+    state[0] += 1
+    _LR[state.data_ptr()] = lr
+
+
+def _replay(p, m, v, g_row, row, step, lr):
+    pr, mr, vr = p[row:row + 1], m[row:row + 1], v[row:row + 1]
+    O.adam_step(pr, np.zeros_like(pr) if g_row is None else g_row[None, :], mr, vr, step, lr)
+
+
+def adam_rows(p, m, v, g, stamp, ids, state, apply, **kw):
+    t, lr = int(state[0]), _LR[state.data_ptr()]
+    P, M, V = _np(p), _np(m), _np(v)
+    for row in np.unique(_np(ids)):
+        for s in range(int(stamp[row]) + 1, t):
+            _replay(P, M, V, None, row, s, lr)
+        if apply:
+            if int(stamp[row]) < t:
+                _replay(P, M, V, _np(g)[row].copy(), row, t, lr)
+                g[row] = 0
+            stamp[row] = t
+        else:
+            stamp[row] = max(int(stamp[row]), t - 1)
+
+
+def adam_flush(p, m, v, stamp, state, **kw):
+    t, lr = int(state[0]), _LR[state.data_ptr()]
+    P, M, V = _np(p), _np(m), _np(v)
+    for row in range(p.shape[0]):
+        for s in range(int(stamp[row]) + 1, t + 1):
+            _replay(P, M, V, None, row, s, lr)
+        stamp[row] = t
+
+
+def gather_pairs(last, hat, loc):
+    return torch.cat([last[loc], hat[loc]], 1)
+
+
+def scatter_grads(g, hat, loc, rows, scale, l2):
+    g.index_add_(0, loc, scale * rows + l2 * hat[loc])
+
+
+def make_step_args(**kw):
+    return kw
+
+
+THETA = [None, None]      # (user net, item net) oracle parameter dicts, set by the test
+
+
+def run_mf_grads(a, d_rows=None, scores=None):
+    """a: the dict of make_step_args; tables are [n, 128] = [last | hat] pairs (table_pitch 128)."""
+    assert a["table_pitch"] == 128 and a["g_theta"] is None, "the stand-in covers the MF path only"
+    u, i, j = _np(a["user"]), _np(a["item"]), _np(a["neg"])
+    ru, ri = _np(a["last_user"]), _np(a["last_item"])
+    r = O.run_mf_forward_backward(THETA[0], THETA[1], ru[u, :64], ru[u, 64:], ri[i, :64], ri[i, 64:],
+                                  ri[j, :64], ri[j, 64:], BCE=True, variant="com")
+    B = len(u)
+    _, rp, rn = step_rows(B)
+    d_rows[:B] = torch.from_numpy(r["d_u_hat"]); d_rows[rp:rp + B] = torch.from_numpy(r["d_i_hat"])
+    d_rows[rn:rn + B] = torch.from_numpy(r["d_j_hat"])
+    a["loss_out"][0] = float(r["loss"])

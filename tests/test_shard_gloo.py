@@ -84,3 +84,66 @@ def test_row_exchange_world1_identity():
     plans = ex.plan_epoch(torch.tensor([3, 3, 9, 0, 7]), [2, 2, 1])
     assert [p.n for p in plans] == [2, 2, 1]
     assert torch.equal(ex.fetch(plans[1], lambda loc: full[loc]), full[torch.tensor([9, 0])])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the whole sharded MF step (exchange + row-lazy Adam bookkeeping + global-batch scaling) on CPU: ShardedSML with the numpy
+# stand-in operators of tests/fake_ops.py, two gloo ranks, against the oracle's dense single-process step
+def _sharded_worker(rank, world, port, out_dir):
+    import types
+    from oracle import sml_oracle as O
+    from sml_b200.shard import ShardedSML
+    from tests import fake_ops
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cfg = _sharded_case()
+        fake_ops.THETA[:] = [cfg["tu"], cfg["ti"]]
+        tr = types.SimpleNamespace(theta=torch.zeros(8), theta_grad=torch.zeros(8), variant=0)
+        T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+        s = ShardedSML(shard_rows(T(cfg["ut"]), world, rank), shard_rows(T(cfg["it"]), world, rank), tr, world=world, rank=rank,
+                       mf_lr=cfg["lr"], l2=cfg["l2"], ops=fake_ops)
+        s.last_user.mul_(0.9); s.last_item.mul_(0.9)                # w_{t-1} != w_hat
+        u, i, j = (T(x[rank]) for x in (cfg["u"], cfg["i"], cfg["j"]))
+        loss = s.mf_epoch(u, i, j, cfg["B"])
+        s.flush()
+        torch.save(dict(user=s.user, item=s.item, m_user=s.m_user, stamp=s.stamp_user, loss=float(loss)), os.path.join(out_dir, "s%d.pt" % rank))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def _sharded_case():
+    from oracle import sml_oracle as O
+    rng = np.random.default_rng(21)
+    U, I, B, n = 37, 53, 12, 12 * 2 + 5                                 # per rank: two full steps and a ragged third
+    return dict(ut=(rng.standard_normal((U, 64)) * 0.3).astype(np.float32), it=(rng.standard_normal((I, 64)) * 0.3).astype(np.float32),
+                tu=O.init_theta(np.random.default_rng(1)), ti=O.init_theta(np.random.default_rng(2)), lr=0.01, l2=1e-4, B=B, n=n,
+                u=[rng.integers(0, 9, n), rng.integers(0, U, n)],         # rank 0 hammers a few users: duplicates + lazy catch-up
+                i=[rng.integers(0, I, n), rng.integers(0, I, n)], j=[rng.integers(0, I, n), rng.integers(0, I, n)])
+
+
+def test_sharded_mf_epoch_world2_matches_dense_oracle(tmp_path):
+    from oracle import sml_oracle as O
+    world = 2
+    mp.spawn(_sharded_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    cfg = _sharded_case()
+    st = dict(last_user=cfg["ut"] * np.float32(0.9), last_item=cfg["it"] * np.float32(0.9), user_tab=cfg["ut"].copy(), item_tab=cfg["it"].copy())
+    for k, ref in (("m_user", "user_tab"), ("v_user", "user_tab"), ("m_item", "item_tab"), ("v_item", "item_tab")):
+        st[k] = np.zeros_like(st[ref])
+    B, n = cfg["B"], cfg["n"]
+    total = 0.0
+    for step, o in enumerate(range(0, n, B), 1):                      # the global batch of a step = both ranks' slices
+        cat = lambda x: np.concatenate([x[0][o:o + B], x[1][o:o + B]])
+        gu, gi, gj = cat(cfg["u"]), cat(cfg["i"]), cat(cfg["j"])
+        l2_term = cfg["l2"] * 0.5 * float((st["user_tab"][gu] ** 2).sum() + (st["item_tab"][gi] ** 2).sum() + (st["item_tab"][gj] ** 2).sum())
+        loss, _, _ = O.sml_mf_step(st, cfg["tu"], cfg["ti"], gu, gi, gj, cfg["lr"], cfg["l2"], step)
+        total += float(loss) - l2_term                                # the sharded step reports the BCE part (like run_MF)
+    parts = [torch.load(os.path.join(str(tmp_path), "s%d.pt" % r)) for r in range(world)]
+    for r, p in enumerate(parts):
+        assert np.abs(p["user"].numpy() - st["user_tab"][r::world]).max() < 2e-6, "user shard %d" % r
+        assert np.abs(p["item"].numpy() - st["item_tab"][r::world]).max() < 2e-6, "item shard %d" % r
+        assert np.abs(p["m_user"].numpy() - st["m_user"][r::world]).max() < 1e-7
+        assert int(p["stamp"].min()) == 3 and int(p["stamp"].max()) == 3
+    # each rank returns the sum over steps of its share of the global-mean BCE loss; the shares add up
+    assert abs(sum(p["loss"] for p in parts) - total) < 1e-4 * abs(total)
