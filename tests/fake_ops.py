@@ -105,3 +105,32 @@ def run_mf_grads(a, d_rows=None, scores=None):
     d_rows[:B] = torch.from_numpy(r["d_u_hat"]); d_rows[rp:rp + B] = torch.from_numpy(r["d_i_hat"])
     d_rows[rn:rn + B] = torch.from_numpy(r["d_j_hat"])
     a["loss_out"][0] = float(r["loss"])
+
+
+# ---- full-catalog evaluation stand-ins (ShardedSML.eval_fullcat) -------------------------------------------
+def pair_scores(user_tab, item_tab, user, item, norm=False):
+    return (user_tab[user] * item_tab[item]).sum(-1)
+
+
+def pack_rows(tab, ids=None):
+    return tab if ids is None else tab[ids]
+
+
+def fullcat_ranks(user_tab, item_tab, users, pos_items, items_packed=None, item_id0=0, n_items=None, gt=None, eq=None, s_pos=None):
+    """Counts over the rows of ``items_packed`` (this rank's shard); pos_items = local row of the positive or -1."""
+    s = user_tab[users] @ items_packed[:n_items].T                      # [n, n_items]
+    keep = torch.ones_like(s, dtype=torch.bool)
+    has = pos_items >= 0
+    keep[torch.nonzero(has).squeeze(1), pos_items[has] - item_id0] = False
+    g = ((s > s_pos[:, None]) & keep).sum(1).to(torch.int32)
+    e = ((s == s_pos[:, None]) & keep).sum(1).to(torch.int32)
+    return g, e
+
+
+def eval_reduce(gt, eq, topk, batch=1024, tie_loses=True):
+    rank = (gt + eq).to(torch.int64)
+    hit = rank < topk
+    nd = torch.where(hit, 1.0 / torch.log2(rank.float() + 2.0), torch.zeros(()))
+    nb = -(-gt.numel() // batch)
+    return (torch.stack([hit[b * batch:(b + 1) * batch].sum() for b in range(nb)]).to(torch.int32),
+            torch.stack([nd[b * batch:(b + 1) * batch].sum() for b in range(nb)]))

@@ -147,3 +147,50 @@ def test_sharded_mf_epoch_world2_matches_dense_oracle(tmp_path):
         assert int(p["stamp"].min()) == 3 and int(p["stamp"].max()) == 3
     # each rank returns the sum over steps of its share of the global-mean BCE loss; the shares add up
     assert abs(sum(p["loss"] for p in parts) - total) < 1e-4 * abs(total)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# sharded full-catalog evaluation (padding, positive-row mapping, count all-reduce, per-rank slices) on CPU
+def _fullcat_case():
+    rng = np.random.default_rng(33)
+    U, I = 41, 203
+    it = rng.standard_normal((I, 64)).astype(np.float32)
+    pairs = [np.stack([rng.integers(0, U, n), rng.integers(0, I, n)], 1) for n in (23, 9)]     # ragged: 23 pairs vs 9
+    ut = rng.standard_normal((U, 64)).astype(np.float32) * 0.2
+    for p in pairs:                                   # users look like their positives: small ranks, many hits
+        ut[p[:, 0]] += it[p[:, 1]]
+    return ut, it, pairs
+
+
+def _fullcat_worker(rank, world, port, out_dir):
+    import types
+    from sml_b200.shard import ShardedSML
+    from tests import fake_ops
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ut, it, pairs = _fullcat_case()
+        T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+        tr = types.SimpleNamespace(theta=torch.zeros(8), theta_grad=torch.zeros(8), variant=0)
+        s = ShardedSML(shard_rows(T(ut), world, rank), shard_rows(T(it), world, rank), tr, world=world, rank=rank, ops=fake_ops)
+        out = s.eval_fullcat(T(pairs[rank]), 5, chunk=8)             # several chunks, the last ones empty on rank 1
+        torch.save(out, os.path.join(out_dir, "f%d.pt" % rank))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_fullcat_world2_matches_bruteforce(tmp_path):
+    world = 2
+    mp.spawn(_fullcat_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    ut, it, pairs = _fullcat_case()
+    allp = np.concatenate(pairs)
+    s = ut[allp[:, 0]] @ it.T
+    sp = (ut[allp[:, 0]] * it[allp[:, 1]]).sum(-1)
+    mask = np.ones_like(s, dtype=bool); mask[np.arange(len(allp)), allp[:, 1]] = False
+    rank = ((s >= sp[:, None]) & mask).sum(1)                        # ties: the positive loses
+    hits = int((rank < 5).sum()); ndcg = float((1.0 / np.log2(rank[rank < 5] + 2.0)).sum())
+    assert hits > 10                                                  # the case is built to have many hits
+    for r in range(world):
+        out = torch.load(os.path.join(str(tmp_path), "f%d.pt" % r))
+        assert int(out[0]) == hits and int(out[2]) == len(allp) and abs(float(out[1]) - ndcg) < 1e-4
