@@ -93,9 +93,35 @@ def make_step_args(**kw):
 THETA = [None, None]      # (user net, item net) oracle parameter dicts, set by the test
 
 
+# flat theta layout of include/sml_b200.h (SML_OFF_*): views into one fp32 block [user net | item net]
+_OFF = {"conv1.weight": 0, "conv1.bias": 32, "conv2.weight": 64, "conv2.bias": 128, "fc1.weight": 160, "fc1.bias": 164000,
+        "fc2.weight": 164512, "fc2.bias": 197280}
+
+
+def flat_theta(tu, ti):
+    """-> (flat torch tensor [2 * NET_STRIDE], (user dict, item dict) of numpy VIEWS into it)."""
+    flat = torch.zeros(2 * NET_STRIDE, dtype=torch.float32)
+    buf = flat.numpy()
+    views = []
+    for n, th in enumerate((tu, ti)):
+        d = {}
+        for k in O.THETA_KEYS:
+            lo = n * NET_STRIDE + _OFF[k]
+            buf[lo:lo + th[k].size] = th[k].ravel()
+            d[k] = buf[lo:lo + th[k].size].reshape(th[k].shape)
+        views.append(d)
+    return flat, views
+
+
+def adam_dense(p, m, v, g, state, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, zero_grad=True):
+    O.adam_step(_np(p), _np(g), _np(m), _np(v), int(state[0]), _LR[state.data_ptr()], weight_decay=weight_decay)
+    if zero_grad:
+        g.zero_()
+
+
 def run_mf_grads(a, d_rows=None, scores=None):
     """a: the dict of make_step_args; tables are [n, 128] = [last | hat] pairs (table_pitch 128)."""
-    assert a["table_pitch"] == 128 and a["g_theta"] is None, "the stand-in covers the MF path only"
+    assert a["table_pitch"] == 128
     u, i, j = _np(a["user"]), _np(a["item"]), _np(a["neg"])
     ru, ri = _np(a["last_user"]), _np(a["last_item"])
     r = O.run_mf_forward_backward(THETA[0], THETA[1], ru[u, :64], ru[u, 64:], ri[i, :64], ri[i, 64:],
@@ -105,6 +131,12 @@ def run_mf_grads(a, d_rows=None, scores=None):
     d_rows[:B] = torch.from_numpy(r["d_u_hat"]); d_rows[rp:rp + B] = torch.from_numpy(r["d_i_hat"])
     d_rows[rn:rn + B] = torch.from_numpy(r["d_j_hat"])
     a["loss_out"][0] = float(r["loss"])
+    if a["g_theta"] is not None:                       # accumulate like the kernels do (the caller zeroed it)
+        gt = _np(a["g_theta"])
+        for n, g in enumerate((r["g_user"], r["g_item"])):
+            for k in O.THETA_KEYS:
+                lo = n * NET_STRIDE + _OFF[k]
+                gt[lo:lo + g[k].size] += np.asarray(g[k], dtype=np.float32).ravel()
 
 
 # ---- full-catalog evaluation stand-ins (ShardedSML.eval_fullcat) -------------------------------------------

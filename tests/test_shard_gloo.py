@@ -107,7 +107,16 @@ def _sharded_worker(rank, world, port, out_dir):
         u, i, j = (T(x[rank]) for x in (cfg["u"], cfg["i"], cfg["j"]))
         loss = s.mf_epoch(u, i, j, cfg["B"])
         s.flush()
-        torch.save(dict(user=s.user, item=s.item, m_user=s.m_user, stamp=s.stamp_user, loss=float(loss)), os.path.join(out_dir, "s%d.pt" % rank))
+        res = dict(user=s.user.clone(), item=s.item.clone(), m_user=s.m_user.clone(), stamp=s.stamp_user.clone(), loss=float(loss))
+        # transfer epoch on the snapshots: theta gradients all-reduced, replicated Adam with coupled L2
+        flat, views = fake_ops.flat_theta(cfg["tu"], cfg["ti"])
+        fake_ops.THETA[:] = views
+        tr.theta, tr.theta_grad = flat, torch.zeros_like(flat)
+        s.m_theta, s.v_theta = torch.zeros_like(flat), torch.zeros_like(flat)
+        s.save_hat()
+        res["tr_loss"] = float(s.tr_epoch(u, i, j, cfg["B"]))
+        res["theta"] = flat.clone()
+        torch.save(res, os.path.join(out_dir, "s%d.pt" % rank))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -147,6 +156,21 @@ def test_sharded_mf_epoch_world2_matches_dense_oracle(tmp_path):
         assert int(p["stamp"].min()) == 3 and int(p["stamp"].max()) == 3
     # each rank returns the sum over steps of its share of the global-mean BCE loss; the shares add up
     assert abs(sum(p["loss"] for p in parts) - total) < 1e-4 * abs(total)
+    # transfer epoch: the oracle's dense single-process steps on the same global batches, snapshots = the tables after the MF epoch
+    tu = {k: v.copy() for k, v in cfg["tu"].items()}; ti = {k: v.copy() for k, v in cfg["ti"].items()}
+    opt = {nm: {k: (np.zeros_like(th[k]), np.zeros_like(th[k])) for k in O.THETA_KEYS} for nm, th in (("user", tu), ("item", ti))}
+    tabs = dict(last_user=st["last_user"], last_item=st["last_item"], user_hat=st["user_tab"], item_hat=st["item_tab"])
+    tr_total = 0.0
+    for step, o in enumerate(range(0, n, B), 1):
+        cat = lambda x: np.concatenate([x[0][o:o + B], x[1][o:o + B]])
+        loss, _, _ = O.sml_tr_step(tu, ti, opt, tabs, cat(cfg["u"]), cat(cfg["i"]), cat(cfg["j"]), 0.001, 1e-4, step)
+        tr_total += float(loss)
+    from tests import fake_ops
+    ref_flat, _ = fake_ops.flat_theta(tu, ti)
+    for p in parts:
+        assert (p["theta"] - ref_flat).abs().max().item() < 2e-5      # Adam on theta: lr 1e-3, noise-sensitive where |g| ~ eps
+    assert torch.equal(parts[0]["theta"], parts[1]["theta"])           # replicas stay identical
+    assert abs(sum(p["tr_loss"] for p in parts) - tr_total) < 1e-4 * abs(tr_total)
 
 
 # ---------------------------------------------------------------------------------------------------------
