@@ -364,6 +364,9 @@ def run_ours(a):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    # "eval" holds only the evaluations that launched the scoring kernel inside the timed region (one launch each; the
+    # evaluations that reuse a kept rank pass are timed as "eval_reused"): achieved = algorithmic bytes per launch / its
+    # average duration (CUDA events around the evaluation: scoring kernel + the 6 us reduce kernel)
     ev_n, ev_ms = phases.get("eval", (0, 0.0))
     per_eval_ms = ev_ms / max(ev_n, 1)
     ach = shape["rows"] * EVAL_BYTES_PER_ROW / max(per_eval_ms, 1e-9) / 1e6

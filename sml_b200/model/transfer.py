@@ -286,11 +286,14 @@ class meta_train(object):
         # of outer phase p+1 repeats the last pass of phase p, model/transfer.py:445 vs :740).  The scoring pass is reused
         # when the same file is evaluated again and no method of this class has touched the MF tables in between
         # (_tab_version); the reference's RNG draw per evaluation is still consumed inside test_model.
+        reused = False
         if isinstance(test_set, DeviceTestSet):
             key = (test_set.rows.data_ptr(), test_set.rows.shape, self._tab_version)
             if self._eval_cache is not None and self._eval_cache[0] == key:
                 test_set._rank_cache, test_set.frozen = self._eval_cache[1], True
-        with self.events("eval"):
+            reused = test_set._rank_cache is not None and test_set.frozen
+        # "eval" = evaluations that launch the scoring kernel, "eval_reused" = those that only reduce a kept rank pass
+        with self.events("eval_reused" if reused else "eval"):
             r = test_model(self.MFbase, test_set, topK=topK)
         if isinstance(test_set, DeviceTestSet) and test_set._rank_cache is not None:
             self._eval_cache = ((test_set.rows.data_ptr(), test_set.rows.shape, self._tab_version), test_set._rank_cache)
