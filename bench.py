@@ -14,9 +14,12 @@ epoch) with the reference's 40 validation passes and 21 full-table transfers (SU
            numpy period arrays: host->device copies of the period files and of every epoch's sampled
            triples, and the device->host reads of every loss / recall / ndcg are inside the timed region.
   roofline / kernels : per-kernel CUDA-event timings taken live inside the timed region.
-  cpu_baseline : oracle/torch_port.py (stock-PyTorch CPU port of the reference loop; /root/reference
-           cannot travel to the GPU box) on a bounded sample, composed to periods/s.
-  --impl reference : the same CPU port as the reference arm.
+  cpu_baseline : the UNMODIFIED reference (baseline/_ref, staged by oracle/stage_reference.py; driven through
+           its own meta_train methods by oracle/ref_arm.py, DataLoader included, --numworkers 0) on the box's host
+           cores, on a bounded sample of every phase composed to one period (kind "reference"); the stock-PyTorch
+           port (oracle/torch_port.py, kind "port") only if the staged tree is missing.
+  torch_cuda_baseline : the same unmodified reference on this B200 through its own torch-CUDA path (TF32 off).
+  --impl reference : the reference arm = that CPU measurement, one bounded sample per step.
 """
 from __future__ import annotations
 
@@ -41,6 +44,15 @@ TRANSFER_FLOP_PER_ROW = 403456
 TRANSFER_BYTES_PER_ROW = 768
 EVAL_NCU_DRAM_BYTES = 655_940_000                          # dram__bytes_read.sum + dram__bytes_write.sum of one 75 000-row launch (ncu --set full, r01)
 EVAL_NCU_DRAM_BYTES_PREFILTER = None                       # same for k_eval_prefilter (filled from profiles/r01_kernels_ncu.md when captured)
+
+
+def bench_config(shape, world):
+    """The workload description: identical keys and values in both arms (same_config)."""
+    return {"workload": "configs[1]: Yelp-shaped SML period stream, ConvTransfer_com, one period per step",
+            "n_users": shape["n_users"], "n_items": shape["n_items"], "rows_per_period": shape["rows"],
+            "candidates_per_eval_row": 1000, **HYPER,
+            "l2_flush": "inputs larger than L2: each step streams 2 x 600 MB period files and 47 MB x 7 table copies",
+            "parallelism": "1 replica stream per GPU" if world > 1 else "single GPU"}
 
 
 def make_args(**over):
@@ -167,28 +179,66 @@ def cpu_port_periods_per_s(shape, seed=0, scale=1.0, verbose=False, device="cpu"
     return 1.0 / t_period, cores, sample, detail
 
 
+def reference_available():
+    from oracle import ref_harness
+    return ref_harness.available()
+
+
 def run_reference_arm(a):
+    """The reference arm: the unmodified reference's own CPU path on all host threads.  One step = one bounded sample
+    of every phase of a period through the reference's own methods, composed to periods/s (a full CPU period takes
+    ~2 minutes; the measured fraction is in the line)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals, t0 = [], time.perf_counter()
-    for s in range(a.warmup + a.steps):
-        v, cores, sample, detail = cpu_port_periods_per_s(YELP, seed=s, scale=0.5)
-        if s >= a.warmup:
-            vals.append(v)
+    shape = dict(YELP)
+    if a.rows:
+        shape["rows"] = a.rows
+    t0 = time.perf_counter()
+    vals, frac = [], []
+    if reference_available():
+        from oracle import ref_arm
+        import torch
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sc = 3.0
+        p = ref_arm.RefPeriod("cpu", shape, seed=0, n_mf=int(12 * sc), n_tr=int(40 * sc), n_ev=int(3072 * sc))
+        for s in range(a.warmup + a.steps):
+            r = p.run()
+            if s >= a.warmup:
+                vals.append(r["periods_per_s"]); frac.append(r["measured_fraction"])
+        kind, sample, detail = "reference", p.sample_text(), r
+    else:
+        for s in range(a.warmup + a.steps):
+            v, cores, sample, detail = cpu_port_periods_per_s(shape, seed=s, scale=0.5)
+            if s >= a.warmup:
+                vals.append(v)
+        kind = "port"
     v = float(np.mean(vals))
     out = {"impl": "reference", "metric": "periods/sec", "value": v, "unit": "periods/s", "n_gpus": a.gpus, "steps": a.steps,
            "warmup": a.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "configs[1]: Yelp-shaped SML period stream, ConvTransfer_com, one period per step",
-                      "n_users": YELP["n_users"], "n_items": YELP["n_items"], "rows_per_period": YELP["rows"],
-                      "candidates_per_eval_row": 1000, **HYPER,
-                      "note": "the reference's operator sequence (oracle/torch_port.py, stock CPU PyTorch, all host threads); each step "
-                              "times a bounded sample of the period's four phases and composes it to one period"},
-           "cpu_baseline": {"value": v, "unit": "periods/s", "cores": cores, "kind": "port", "sample": sample},
+           "dtype": "f32", "data": "synthetic", "config": bench_config(shape, max(a.gpus, 1)),
+           "note": "the UNMODIFIED reference (baseline/_ref) on the host cores through its own meta_train methods; each step times a "
+                   "bounded sample of the period's four phases and composes one period from the step counts"
+                   if kind == "reference" else "stock-PyTorch port of the reference loop (staged reference tree missing)",
+           "cpu_baseline": {"value": v, "unit": "periods/s", "cores": cores, "kind": kind, "sample": sample,
+                            "measured_fraction_of_a_period": float(np.mean(frac)) if frac else None, "detail": detail},
            "e2e": {"value": v, "unit": "periods/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
     print(json.dumps(out))
+
+
+def reference_leg(device, scale, timeout=600):
+    """oracle/ref_arm.py in a subprocess (its harness monkey-patches torch): the unmodified reference on ``device``."""
+    try:
+        r = subprocess.run([sys.executable, "-m", "oracle.ref_arm", "--device", device, "--scale", str(scale)], cwd=ROOT,
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not line:
+            return {"unavailable": (r.stderr.strip().splitlines() or ["no output"])[-1][:300]}
+        return json.loads(line[-1])
+    except Exception as e:                                   # noqa: BLE001 -- a missing baseline must not kill the bench line
+        return {"unavailable": repr(e)[:300]}
 
 
 # --------------------------------------------------------------------------------------------
@@ -392,10 +442,7 @@ def run_ours(a):
         "metric": "periods/sec", "value": value, "unit": "periods/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": dev_s / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "configs[1]: Yelp-shaped SML period stream, ConvTransfer_com, one period per step",
-                   "n_users": U, "n_items": I, "rows_per_period": shape["rows"], "candidates_per_eval_row": 1000, **HYPER,
-                   "l2_flush": "inputs larger than L2: each step streams 2 x 600 MB period files and 47 MB x 7 table copies",
-                   "parallelism": "1 replica stream per GPU" if world > 1 else "single GPU"},
+        "config": bench_config(shape, world),
         "samples_per_s": world * K * (HYPER["multi_num"] * shape["rows"] * (HYPER["MF_epochs"] + HYPER["TR_epochs"])) / dev_s,
         "e2e": {"value": (world * K / e2e_s) if e2e_s == e2e_s else None, "unit": "periods/s", "h2d_bytes_per_step": int(e2e_h2d),
                 "d2h_bytes_per_step": int(e2e_d2h), "mode": "meta_train(device_sampler=True): host period files, batches sampled on the GPU"},
@@ -421,12 +468,22 @@ def run_ours(a):
     }
     if rank == 0:
         if world == 1 and not a.no_cpu_baseline:
-            v, cores, sample, detail = cpu_port_periods_per_s(YELP, seed=0, scale=1.0)
-            out["cpu_baseline"] = {"value": v, "unit": "periods/s", "cores": cores, "kind": "port", "sample": sample, "detail": detail}
-            # second bar: the same stock-PyTorch operator sequence on this B200 (cuBLAS / cuDNN / ATen)
-            v2, _, sample2, detail2 = cpu_port_periods_per_s(YELP, seed=0, scale=4.0, device="cuda")
-            out["torch_cuda_baseline"] = {"value": v2, "unit": "periods/s", "kind": "port (stock PyTorch eager on the same GPU, TF32 off)",
-                                          "sample": sample2, "detail": detail2}
+            del meta
+            torch.cuda.empty_cache()
+            if reference_available():
+                r = reference_leg("cpu", 3.0)
+                if "unavailable" not in r:
+                    out["cpu_baseline"] = {"value": r["periods_per_s"], "unit": "periods/s", "cores": r["cores"], "kind": "reference",
+                                           "sample": r["sample"], "measured_fraction_of_a_period": r["measured_fraction"], "detail": r}
+                # second bar: the unmodified reference on this B200 through its own torch-CUDA path
+                r2 = reference_leg("cuda", 1.0)
+                out["torch_cuda_baseline"] = ({"value": r2["periods_per_s"], "unit": "periods/s", "sample": r2["sample"],
+                                               "kind": "reference (its own torch-CUDA path on the same GPU, TF32 off, numworkers 0)",
+                                               "measured_fraction_of_a_period": r2["measured_fraction"], "detail": r2}
+                                              if "unavailable" not in r2 else r2)
+            if "cpu_baseline" not in out:
+                v, cores, sample, detail = cpu_port_periods_per_s(YELP, seed=0, scale=1.0)
+                out["cpu_baseline"] = {"value": v, "unit": "periods/s", "cores": cores, "kind": "port", "sample": sample, "detail": detail}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

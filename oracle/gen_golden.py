@@ -265,7 +265,19 @@ def gen_period_run(ns, stop=False, news=False):
                                float(sum(p.double().abs().sum() for p in meta.transfer.parameters()))])
         return flag
     meta.train_one_stage3 = wrapped
+    # every test_model call of the run, in order: (topK, rows, recall, ndcg) -- model/transfer.py:444-446,517-519,
+    # 684-686,738-741 (validation passes) and :810-823,855-868 (the real test at K = 20, 10, 5)
+    eval_log = []
+    tm = ns.transfer.test_model
+
+    def logged_test_model(model, test_set, *a, **k):
+        r, n = tm(model, test_set, *a, **k)
+        eval_log.append([float(k.get("topK", 10)), float(len(test_set.dataset)), float(r), float(n)])
+        return r, n
+    ns.transfer.test_model = logged_test_model
     meta.run(args)
+    ns.transfer.test_model = tm
+    out["eval_log"] = np.array(eval_log, dtype=np.float64).reshape(-1, 4)
     out["stage_sums"] = np.array(stage_sums)
     out["final_user"] = meta.MFbase.user_laten.weight.detach().numpy().copy()
     out["final_item"] = meta.MFbase.item_laten.weight.detach().numpy().copy()

@@ -9,34 +9,56 @@ touching the reference sources:
   (3) ``evaluation2.test_model`` returns a numpy scalar on modern numpy and the caller
       does ``ndcg.cpu()`` (model/transfer.py:813) -> wrap to return a tensor;
   (4) ``--numworkers 0``.
-/root/reference does not exist on the GPU box; nothing under tests -m gpu, smoke() or
-bench.py imports this file.
+  (5) on CUDA: TF32 off for cuDNN / matmul so that conv1 / conv2 are fp32 like the CPU path, and
+      ``MFbasemode.test`` hands its per-batch NDCG back on the host (``np.array([cuda tensors])``
+      in evalution/evaluation2.py:24-25 refuses device tensors).
+Search order for the tree: $SML_REFERENCE, /root/reference (build container), baseline/_ref (the
+staged copy that travels to the GPU box, oracle/stage_reference.py).  Only bench.py's reference /
+cpu_baseline legs (through oracle/ref_arm.py, in a subprocess) and oracle/gen_golden.py import this
+file; nothing under sml_b200/ does.
 """
 from __future__ import annotations
 
 import os
 import sys
 
-REF = os.environ.get("SML_REFERENCE", "/root/reference")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find():
+    for c in (os.environ.get("SML_REFERENCE"), "/root/reference", os.path.join(_ROOT, "baseline", "_ref")):
+        if c and os.path.isdir(os.path.join(c, "model")):
+            return c
+    return os.environ.get("SML_REFERENCE", "/root/reference")
+
+
+REF = _find()
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REF, "model"))
 
 
-def load():
+def load(device=None):
     """Returns a namespace with the reference modules (MF, conv_transfer, transfer,
-    evaluation2, evaluation, evalution_function, dataset, dataset2, main_yelp)."""
+    evaluation2, evaluation, evalution_function, dataset, dataset2, main_yelp).
+    ``device``: "cpu" forces the CPU path even when a GPU is present (shim 1), "cuda" runs the
+    reference's own torch-CUDA path (shim 5); default: cpu unless CUDA is available."""
     import types
     import torch
     if not available():
         raise RuntimeError("reference tree not present at %s" % REF)
     if REF not in sys.path:
         sys.path.insert(0, REF)
-    if not torch.cuda.is_available():
+    if device is None:
+        device = "cuda" if torch.cuda.is_available() else "cpu"
+    if device == "cpu":
         torch.Tensor.cuda = lambda self, *a, **k: self           # shim (1)
         torch.nn.Module.cuda = lambda self, *a, **k: self
         torch.cuda.manual_seed = lambda *a, **k: None
+    else:
+        torch.backends.cudnn.allow_tf32 = False                  # shim (5)
+        torch.backends.cuda.matmul.allow_tf32 = False
     _orig_load = torch.load
 
     def _load(*a, **k):                                          # shim (2)
@@ -56,6 +78,14 @@ def load():
     ns.transfer = importlib.import_module("model.transfer")
     ns.main_yelp = importlib.import_module("main_yelp")
     ns.main_news = importlib.import_module("main_news")
+
+    if device != "cpu":                                          # shim (5): per-batch NDCG back on the host
+        _test = ns.MF.MFbasemode.test
+
+        def _test_host(self, *a, **k):
+            h, n, idx = _test(self, *a, **k)
+            return h, (n.cpu() if torch.is_tensor(n) else n), idx
+        ns.MF.MFbasemode.test = _test_host
 
     _tm = ns.evaluation2.test_model
 

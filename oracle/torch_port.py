@@ -72,7 +72,7 @@ class Port(object):
         loss = loss + self.l2 * (0.5 * torch.sum(wu ** 2 + wi ** 2 + wj ** 2))
         loss.backward()
         self.mf_opt.step()
-        return float(loss.detach())
+        return loss.detach()            # stays on the device like the reference's loss_all accumulation (model/transfer.py:501,722)
 
     def tr_step(self, u, i, j):                                 # model/transfer.py:701-728
         u, i, j = (torch.as_tensor(x).long().to(self.device) for x in (u, i, j))
@@ -81,7 +81,7 @@ class Port(object):
                       self.last_item[j], self.item_hat[j])
         loss.backward()
         self.tr_opt.step()
-        return float(loss.detach())
+        return loss.detach()            # stays on the device like the reference's loss_all accumulation (model/transfer.py:501,722)
 
     def save_last(self):                                        # model/transfer.py:925-927
         self.last_user.copy_(self.user.weight.data); self.last_item.copy_(self.item.weight.data)

@@ -91,16 +91,23 @@ class transfer_data(object):
         self.item_number = information[2]
         print(information)
         self._cache = {}
+        self.cache_files = 6                       # np.load results kept (LRU): periods t and t+1, train + test
 
     def reinit(self):
         self.test_count = 0
         self.start_test_time = copy.deepcopy(self.online_test_time)
 
     def _load(self, kind, name):
+        # only periods t and t+1 are ever re-read within a stage (set_t / set_tt / val / now_test): keep the last few
+        # files (LRU) instead of the whole stream (a Yelp-shaped test file is ~600 MB of int64)
         key = (kind, name)
-        if key not in self._cache:
-            self._cache[key] = np.load(self.path + self.dataname + "/" + kind + "/" + name + ".npy")
-        return self._cache[key]
+        hit = self._cache.pop(key, None)
+        if hit is None:
+            hit = np.load(self.path + self.dataname + "/" + kind + "/" + name + ".npy")
+        self._cache[key] = hit
+        while len(self._cache) > self.cache_files:
+            self._cache.pop(next(iter(self._cache)))
+        return hit
 
     def _set_t(self, now_time):
         if self.MF_sample == "alone":

@@ -196,6 +196,7 @@ class meta_train(object):
         self.graph_launches = 0                    # kernels executed through graph replays (not seen by sml_launch_count)
         self._tab_version = 0                      # bumped by every method that writes the MF tables
         self._eval_cache = None
+        self.eval_passes = dict(scored=0, reused=0)   # evaluations that launched the scoring kernel / reused a kept pass
         self.events = EventTimers(False)           # CUDA-event phase timers (bench.py switches them on)
 
         self.recall = []
@@ -280,23 +281,38 @@ class meta_train(object):
         return [x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.int64)).to(self.device)
                 for x in arrs]
 
+    def invalidate(self):
+        """Call after writing the MF tables from OUTSIDE this class through a path torch cannot see
+        (``MFbase.*.weight.data`` edits, raw-pointer kernels): drops every kept evaluation pass.  Writes through
+        this class's own methods, ``load_state_dict`` / in-place ops on the Parameters themselves are tracked."""
+        self._tab_version += 1
+        self._eval_cache = None
+
+    def _tables_key(self):
+        uw, iw = self.MFbase.user_laten.weight, self.MFbase.item_laten.weight
+        return (self._tab_version, uw.data_ptr(), iw.data_ptr(), uw._version, iw._version)
+
     def _eval(self, test_set, topK):
         t0 = time.perf_counter()
         # The reference re-scores a file even when nothing changed since its last evaluation (the "before train MF" pass
-        # of outer phase p+1 repeats the last pass of phase p, model/transfer.py:445 vs :740).  The scoring pass is reused
-        # when the same file is evaluated again and no method of this class has touched the MF tables in between
-        # (_tab_version); the reference's RNG draw per evaluation is still consumed inside test_model.
+        # of outer phase p+1 repeats the last pass of phase p, model/transfer.py:445 vs :740; the three K of the real
+        # test, :855-868).  A scoring pass is reused ONLY when the very same device file is evaluated again and nothing
+        # has written the MF tables in between; the decision is taken afresh on every call (a hit never outlives the
+        # call that found it), and the reference's RNG draw per evaluation is still consumed inside test_model.
         reused = False
         if isinstance(test_set, DeviceTestSet):
-            key = (test_set.rows.data_ptr(), test_set.rows.shape, self._tab_version)
-            if self._eval_cache is not None and self._eval_cache[0] == key:
-                test_set._rank_cache, test_set.frozen = self._eval_cache[1], True
-            reused = test_set._rank_cache is not None and test_set.frozen
+            c = self._eval_cache
+            reused = c is not None and c[0] is test_set.rows and c[1] == self._tables_key()
+            test_set._rank_cache = c[2] if reused else None
+            test_set.frozen = reused
         # "eval" = evaluations that launch the scoring kernel, "eval_reused" = those that only reduce a kept rank pass
         with self.events("eval_reused" if reused else "eval"):
             r = test_model(self.MFbase, test_set, topK=topK)
-        if isinstance(test_set, DeviceTestSet) and test_set._rank_cache is not None:
-            self._eval_cache = ((test_set.rows.data_ptr(), test_set.rows.shape, self._tab_version), test_set._rank_cache)
+        if isinstance(test_set, DeviceTestSet):
+            test_set.frozen = False
+            if test_set._rank_cache is not None:      # the cache holds the file tensor itself: no address aliasing
+                self._eval_cache = (test_set.rows, self._tables_key(), test_set._rank_cache)
+        self.eval_passes["reused" if reused else "scored"] += 1
         self.timers["eval"] += time.perf_counter() - t0
         return r
 
@@ -361,7 +377,11 @@ class meta_train(object):
                                       adam_state=self.MF_optimizer.adam_state, lr=lr, l2=args.l2, loss_out=self._loss,
                                       workspace=ws, **self._mf, **self._stamps)
         self._tab_version += 1
-        self._run_epoch("mf", build, (user, item, neg), n, B, (lr, args.l2, uw.data_ptr(), iw.data_ptr()))
+        # every pointer / scalar baked into the captured StepArgs is part of the graph key
+        self._run_epoch("mf", build, (user, item, neg), n, B,
+                        (lr, args.l2, self.transfer.variant) + tuple(t.data_ptr() for t in (
+                            uw, iw, self.last_user_weight, self.last_item_weight, self.transfer.theta, ws,
+                            self.MF_optimizer.adam_state, *self._mf.values(), *self._stamps.values())))
         return self._loss[1].item() / nb
 
     # ------------------------------------------------------------------ transfer (outer) training
@@ -463,15 +483,18 @@ class meta_train(object):
                                       adam_state=self.transfer_optimizer.adam_state, lr=g["lr"], l2=g["weight_decay"],
                                       g_theta=self.transfer.theta_grad, m_theta=self._tr["m"], v_theta=self._tr["v"],
                                       loss_out=self._loss, workspace=ws)
-        self._run_epoch("tr", build, (user, item, neg), n, B, (g["lr"], g["weight_decay"], self.transfer.theta.data_ptr()))
+        self._run_epoch("tr", build, (user, item, neg), n, B,
+                        (g["lr"], g["weight_decay"], self.transfer.variant) + tuple(t.data_ptr() for t in (
+                            self.transfer.theta, self.transfer.theta_grad, self._tr["m"], self._tr["v"], ws,
+                            self.last_user_weight, self.last_item_weight, self.user_weight_hat, self.item_weight_hat,
+                            self.transfer_optimizer.adam_state)))
         return self._loss[1].item() / nb
 
     # ------------------------------------------------------------------ one period
     def _real_test(self, now_test_arr):
         """The three test_model calls at K = 20, 10, 5 (model/transfer.py:810-823,855-868)."""
         self.test_num.append(now_test_arr.shape[0])
-        now_test = self._test_set(now_test_arr)
-        now_test.frozen = True                      # three K on unchanged tables: one scoring pass
+        now_test = self._test_set(now_test_arr)       # three K on unchanged tables: _eval keeps one scoring pass
         for K, rl, nl, tag in ((20, self.recall, self.ndcg, ""), (10, self.recall_10, self.ndcg_10, " @10"),
                                (5, self.recall_5, self.ndcg_5, " @5")):
             recall, ndcg = self._eval(now_test, K)

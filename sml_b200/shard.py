@@ -139,6 +139,10 @@ class ShardedSML(object):
         if ops is None:
             from . import ops
         self.ops = ops
+        if getattr(transfer, "variant", ops.VARIANT_COM) != ops.VARIANT_COM:
+            # ConvTransfer (variant CONV) trains with the BPR loss and an L2-normalised user output
+            # (model/conv_transfer.py:57-85); the sharded steps below hard-wire ConvTransfer_com's BCE path
+            raise NotImplementedError("ShardedSML supports ConvTransfer_com only (the reference default, --transfer_type conv_com)")
         self.world, self.rank, self.group = world, rank, group
         self.ex = RowExchange(world, rank, group)
         z = torch.zeros_like
@@ -202,8 +206,13 @@ class ShardedSML(object):
         n = user.numel()
         sizes = [min(B, n - o) for o in range(0, n, B)]
         if self.world > 1:
+            ns = torch.tensor([len(sizes), -len(sizes)], dtype=torch.int64, device=user.device)
+            dist.all_reduce(ns, op=dist.ReduceOp.MAX, group=self.group)
+            if int(ns[0]) != -int(ns[1]):
+                raise ValueError("sharded epoch: ranks disagree on the step count (%d..%d); give every rank the same number "
+                                 "of batches (pad or trim the per-rank triples)" % (-int(ns[1]), int(ns[0])))
             t = torch.tensor(sizes, dtype=torch.int64, device=user.device)
-            dist.all_reduce(t, group=self.group)                   # global batch of every step (same step count everywhere)
+            dist.all_reduce(t, group=self.group)                   # global batch of every step
         pu = self.ex.plan_epoch(user, sizes)
         it = torch.cat([torch.cat([item[o:o + b], neg[o:o + b]]) for o, b in zip(range(0, n, B), sizes)]) if n else item
         pi = self.ex.plan_epoch(it, [2 * b for b in sizes])

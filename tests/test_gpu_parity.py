@@ -68,6 +68,29 @@ def test_eval_golden(golden, dev):
     assert rel_err(sc.cpu().numpy().reshape(g["scores"].shape), g["scores"]) < FWD_TOL
 
 
+def test_legacy_eval_golden(golden, dev):
+    """evalution/evaluation.py:7-60 (per-user lists, positives first) through the CUDA pair-score kernel against the
+    reference's own output on the same tables (tests/golden/eval.npz: legacy)."""
+    from sml_b200.model.MF import MFbasemode
+    from sml_b200.evalution import evaluation
+    g = golden("eval")
+    with torch.random.fork_rng(devices=[]):
+        mf = MFbasemode(30, 200, 64).to(dev)
+    mf.user_laten.weight.data.copy_(T(g["user"], dev)); mf.item_laten.weight.data.copy_(T(g["legacy_item"], dev))
+    users, pos, negs = [1, 2], [[3, 4], [5]], [list(range(10, 40)), list(range(50, 80))]
+    res = [float(x) for x in evaluation.test_model(mf, (users, pos, negs), topK=5)]
+    ref = g["legacy"]
+    assert res[0] == 0 and res[2] == 0 and res[4] == 0 and ref[0] == 0 and ref[2] == 0 and ref[4] == 0
+    assert abs(res[1] - ref[1]) < 1e-7 and abs(res[3] - ref[3]) < 1e-6, (res, ref)
+    # and against the oracle's restatement user by user, at a K that cuts into the positives
+    for u, p, n in zip(users, pos, negs):
+        s = g["legacy_item"][np.array(p + n)] @ g["user"][u]
+        for K in (1, 3, 5, 10):
+            ro, do = O.legacy_rec_ndcg(s, len(p), K)
+            _, rg, _, dg, _ = evaluation.evalution_for_user(mf, u, p, n, K)
+            assert abs(float(rg) - ro) < 1e-7 and abs(float(dg) - do) < 1e-6, (u, K)
+
+
 def test_eval_vs_oracle_c1000_and_edges(dev):
     from sml_b200 import ops
     rng = np.random.default_rng(1)

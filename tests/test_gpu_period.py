@@ -39,6 +39,14 @@ def run_ours(g, tmp, stop, replay, news=False):
     sd = {("user_transfer." + k): torch.from_numpy(v) for k, v in tu.items()}
     sd.update({("item_transfer." + k): torch.from_numpy(v) for k, v in ti.items()})
     meta.transfer.load_state_dict(sd)
+    meta.eval_log = []
+    inner = meta._eval
+
+    def logged(test_set, topK):
+        r, n = inner(test_set, topK)
+        meta.eval_log.append([float(topK), float(len(test_set)), float(r), float(n)])
+        return r, n
+    meta._eval = logged
     meta.run(args)
     return meta
 
@@ -74,6 +82,23 @@ def test_period_run_matches_reference(golden, tmp_path, name, stop, replay):
     for key in ("ndcg", "ndcg_10", "ndcg_5"):
         got = np.array([float(x) for x in getattr(meta, key)])
         assert np.abs(got - g[key]).max() < (1.2e-2 if not name.endswith("news") else 3e-2), (key, got, g[key])
+    # EVERY test_model call of the reference's run (validation passes before / after each MF epoch and each transfer epoch,
+    # model/transfer.py:444-446,517-519,684-686,738-741, and the real tests): same sequence of (K, rows), metrics within one
+    # borderline row.  A stale (re-used but outdated) scoring pass shows up here as a repeated value.
+    ours, ref = np.array(meta.eval_log), g["eval_log"]
+    assert ours.shape == ref.shape, (ours.shape, ref.shape)
+    assert np.array_equal(ours[:, :2], ref[:, :2])
+    flips = 1.0 if not name.endswith("news") else 3.0
+    assert np.abs(ours[:, 2] - ref[:, 2]).max() <= flips / 96 + 1e-9, np.abs(ours[:, 2] - ref[:, 2]).max()
+    assert np.abs(ours[:, 3] - ref[:, 3]).max() < (1.2e-2 if not name.endswith("news") else 3e-2)
+    first = slice(0, 8)         # the first period's validation passes: before any drift, exact recall
+    assert np.array_equal(np.round(ours[first, 2] * 96), np.round(ref[first, 2] * 96)), (ours[first, 2], ref[first, 2])
+    assert np.abs(ours[first, 3] - ref[first, 3]).max() < 1e-4
+    # scoring passes really launched: everything except the repeats on unchanged tables (the "before MF" pass of outer
+    # phases >= 1, and K = 10 / 5 / the following "before transfer" pass after a real test)
+    assert meta.eval_passes["scored"] + meta.eval_passes["reused"] == len(ref)
+    changed = 1 + int(np.sum(np.any(ref[1:, 2:] != ref[:-1, 2:], axis=1)))
+    assert meta.eval_passes["scored"] >= changed, (meta.eval_passes, changed)
     # Adam step counters: one per optimizer step, surviving across periods (model/transfer.py:764)
     n_mf = sum(len(g["log%d" % n]) for n, k in enumerate(g["log_kinds"]) if str(k) == "MF") // 96 * 3
     assert meta.MF_optimizer.step_count == n_mf

@@ -238,3 +238,62 @@ def test_select_neg_forinteraction_matches_reference(golden, tmp_path):
         assert np.array_equal(np.load(str(base / "test" / ("%d.npy" % k))), g["test%d" % k])
         # the defining properties: negatives distinct, never the row's own history
         assert all(len(set(r[2:])) == int(g["neg_num"]) and r[1] not in r[2:] for r in t)
+
+
+def test_eval_cache_never_serves_stale_ranks(monkeypatch):
+    """meta_train._eval (CPU: the scoring pass is stubbed).  A kept rank pass may only be reused when the same device
+    file is evaluated again with NO table write in between: the reference re-scores every time
+    (model/transfer.py:444-446,517-519,684-686,738-741).  Round-1 bug: a cache hit left ``frozen`` set, so the
+    after-epoch evaluation of every outer phase >= 1 returned the pre-epoch ranks (9 of 31 passes per period)."""
+    import types
+    import torch
+    from sml_b200.model import transfer as T
+    from sml_b200.evalution.evaluation2 import DeviceTestSet
+    from sml_b200.profiling import EventTimers
+
+    m = T.meta_train.__new__(T.meta_train)
+    w = lambda: types.SimpleNamespace(weight=torch.nn.Parameter(torch.zeros(2, 2)))
+    m.MFbase = types.SimpleNamespace(user_laten=w(), item_laten=w())
+    m._tab_version, m._eval_cache = 0, None
+    m.eval_passes = dict(scored=0, reused=0)
+    m.events = EventTimers(False)
+    m.timers = dict(eval=0.0)
+    seen = []
+
+    def fake_test_model(model, ts, topK=10):
+        # what DeviceTestSet.ranks does, with the table version standing in for the scores
+        if not (ts.frozen and ts._rank_cache is not None):
+            ts._rank_cache = ("ranks@", m._tab_version)
+        seen.append(ts._rank_cache[1])
+        return 0.0, torch.tensor(0.0)
+    monkeypatch.setattr(T, "test_model", fake_test_model)
+
+    def file_set(rows):
+        ts = DeviceTestSet.__new__(DeviceTestSet)
+        ts.rows, ts.frozen, ts._rank_cache = rows, False, None
+        return ts
+    val_rows, test_rows = torch.zeros(3, 4, dtype=torch.int64), torch.zeros(3, 4, dtype=torch.int64)
+    multi_num = 10
+    for phase in range(multi_num):                      # one period of train_one_stage3, MF_epochs = TR_epochs = 1
+        val = file_set(val_rows)                        # MF_train_onestage builds one DeviceTestSet for before + after
+        m._eval(val, 20); assert seen[-1] == m._tab_version
+        m._tab_version += 1                             # _mf_epoch
+        m._eval(val, 20); assert seen[-1] == m._tab_version, "after-epoch evaluation served pre-epoch ranks"
+        m._tab_version += 1                             # updata
+        if phase == 0:                                  # the real test: three K on unchanged tables
+            for K in (20, 10, 5):
+                m._eval(file_set(test_rows), K); assert seen[-1] == m._tab_version
+        now = file_set(val_rows)                        # transfer_train_onestage
+        m._eval(now, 20); assert seen[-1] == m._tab_version
+        m._tab_version += 1                             # updata after the transfer epoch
+        m._eval(now, 20); assert seen[-1] == m._tab_version
+    # 40 validation passes of which only the 9 "before MF" repeats of phases >= 1 may be reused, + 1 of the 3 real tests
+    assert m.eval_passes == dict(scored=31 + 1, reused=9 + 2), m.eval_passes
+    # a write torch can see (in-place op on the Parameter) and an explicit invalidate() both force a new pass
+    ts = file_set(val_rows)
+    m._eval(ts, 20); assert m.eval_passes["reused"] == 12
+    with torch.no_grad():
+        m.MFbase.user_laten.weight.add_(1.0)
+    m._eval(ts, 20); assert m.eval_passes["scored"] == 33
+    m.invalidate()
+    m._eval(ts, 20); assert m.eval_passes["scored"] == 34
