@@ -296,6 +296,26 @@ int sml_plain_mf_grads(const float *user_tab, const float *item_tab, const float
                        double l2_i, float *g_user, float *g_item, float *g_item_bias, float *loss_out,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* The whole plain-MF step in ONE kernel (north_star item 1): 128-bit row gather, half-warp dot products, BCE-mean
+ * (model/baseline.py:188-201) or BPR-sum (model/MF.py:141-144 without the bias tables) loss, row gradients with the L2
+ * term, and Adam on exactly the rows of the batch -- no table-sized gradient buffer, no second launch.
+ *   optimizer = SML_OPT_ADAM_DENSE_EXACT: the reference's DENSE torch.optim.Adam (model/baseline.py:111) in its row-lazy
+ *       bit-identical form (see sml_adam_rows): adam_state must carry the history ring, stamp_* the per-row stamps;
+ *       call sml_adam_flush before reading a table as a whole;
+ *   optimizer = SML_OPT_ADAM_SPARSE: only the rows of the batch move, moments decay only when touched (lazy Adam of
+ *       large embedding tables; NOT the reference's semantic -- scaled throughput runs); stamp_* may be null.
+ * head_user / head_item: int32 [n_users] / [n_items] list heads, all -1 on entry and on exit (duplicates of a row inside
+ * the batch are chained through them).  The step counter in adam_state is advanced by the kernel (no sml_adam_tick).
+ * loss_out[0] = this step's loss, loss_out[1] += loss.  workspace: sml_plain_mf_step_workspace_bytes(batch) bytes. */
+#define SML_OPT_ADAM_DENSE_EXACT 0
+#define SML_OPT_ADAM_SPARSE 1
+size_t sml_plain_mf_step_workspace_bytes(int64_t batch);
+int sml_plain_mf_step(float *user_tab, float *item_tab, float *m_user, float *v_user, float *m_item, float *v_item,
+                      int32_t *stamp_user, int32_t *stamp_item, int32_t *head_user, int32_t *head_item, const int64_t *user,
+                      const int64_t *item, const int64_t *neg, int64_t batch, int d, int loss, double l2_u, double l2_i,
+                      int64_t *adam_state, double lr, int optimizer, float *loss_out, void *workspace, size_t workspace_bytes,
+                      void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@ OFF_F1W, OFF_F1B, OFF_F2W, OFF_F2B = 160, 164000, 164512, 197280
 NET_STRIDE = 197344
 VARIANT_COM, VARIANT_CONV = 3, 2
 LOSS_BCE, LOSS_BPR = 0, 1
+OPT_ADAM_DENSE_EXACT, OPT_ADAM_SPARSE = 0, 1
 
 _vp, _i64, _i32, _dbl, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_size_t
 
@@ -75,6 +76,8 @@ _PROTOS = {
     "sml_debug_set_ksplit": (_i32, [_i32, _i32, _i32, _i32]),
     "sml_debug_ksplit": (_i32, [_i32]),
     "sml_debug_gemm": (_i32, [_vp, _vp, _vp, _vp, _vp] + [_i32] * 12 + [_vp]),
+    "sml_plain_mf_step_workspace_bytes": (_sz, [_i64]),
+    "sml_plain_mf_step": (_i32, [_vp] * 13 + [_i64, _i32, _i32, _dbl, _dbl, _vp, _dbl, _i32, _vp, _vp, _sz, _vp]),
     "sml_plain_mf_grads": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 

@@ -11,7 +11,8 @@ import os
 import torch
 
 from . import _lib
-from ._lib import (D, NET_STRIDE, VARIANT_COM, VARIANT_CONV, LOSS_BCE, LOSS_BPR, StepArgs, check, lib, ptr, stream)
+from ._lib import (D, NET_STRIDE, VARIANT_COM, VARIANT_CONV, LOSS_BCE, LOSS_BPR, OPT_ADAM_DENSE_EXACT, OPT_ADAM_SPARSE, StepArgs,
+                   check, lib, ptr, stream)
 
 EVAL_BATCH = 1024      # evaluation2.test_model's DataLoader batch (model/transfer.py:431-435 of the reference)
 
@@ -273,3 +274,22 @@ def plain_mf_grads(user_tab, item_tab, user, item, neg, g_user, g_item, loss_out
                                    ptr(_i64(neg, "neg")), user.numel(), user_tab.shape[1], loss, l2_u, l2_i, ptr(g_user),
                                    ptr(g_item), ptr(g_item_bias), ptr(loss_out), ptr(ws), ws.numel(), stream()),
           "plain_mf_grads")
+
+
+def new_list_heads(n_rows, device):
+    """int32 [n_rows] per-row occurrence-list heads for plain_mf_step (all -1 between steps)."""
+    return torch.full((n_rows,), -1, dtype=torch.int32, device=device)
+
+
+def plain_mf_step(user_tab, item_tab, m_user, v_user, m_item, v_item, head_user, head_item, user, item, neg, adam_state, lr,
+                  loss_out, loss=LOSS_BCE, l2_u=0.0, l2_i=0.0, optimizer=OPT_ADAM_DENSE_EXACT, stamp_user=None, stamp_item=None):
+    """One fused plain-MF step (gather - dot - loss - row gradients + L2 - Adam on the batch rows) in one kernel.
+    OPT_ADAM_DENSE_EXACT needs ``adam_state = new_adam_state(dev, history=True)`` and row stamps; flush with
+    ``adam_flush`` before reading the tables as a whole."""
+    B = user.numel()
+    ws = _workspace(lib().sml_plain_mf_step_workspace_bytes(B), user_tab.device, "plain_mf_step")
+    check(lib().sml_plain_mf_step(ptr(_f32(user_tab, "user_tab")), ptr(_f32(item_tab, "item_tab")), ptr(m_user), ptr(v_user), ptr(m_item),
+                                  ptr(v_item), ptr(stamp_user), ptr(stamp_item), ptr(_i32t(head_user, "head_user")),
+                                  ptr(_i32t(head_item, "head_item")), ptr(_i64(user, "user")), ptr(_i64(item, "item")),
+                                  ptr(_i64(neg, "neg")), B, user_tab.shape[1], loss, float(l2_u), float(l2_i), ptr(adam_state), float(lr),
+                                  optimizer, ptr(loss_out), ptr(ws), ws.numel(), stream()), "plain_mf_step")

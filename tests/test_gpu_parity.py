@@ -292,6 +292,101 @@ def test_plain_mf_vs_oracle(dev):
     assert np.abs(p.cpu().numpy() - pn).max() < 1e-5 and float(g_u.abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("loss_kind", ["bce", "bpr"])
+def test_plain_mf_fused_step_vs_oracle(dev, loss_kind):
+    """sml_plain_mf_step (gather - dot - loss - row gradients + L2 - Adam in one kernel) against the oracle's
+    plain-MF gradients followed by DENSE Adam on whole tables (model/baseline.py:111,188-201), over several steps with
+    duplicate ids inside a batch, rows that skip steps (row-lazy replay) and rows never touched."""
+    from sml_b200 import ops
+    rng = np.random.default_rng(11)
+    U, I, B, steps = 300, 400, 333, 9
+    ut = (0.3 * rng.standard_normal((U, 64))).astype(np.float32); it = (0.3 * rng.standard_normal((I, 64))).astype(np.float32)
+    l2u, l2i, lr = (1e-3, 2e-3, 0.01) if loss_kind == "bce" else (0.0, 0.0, 0.01)
+    pu, pi = T(ut, dev), T(it, dev)
+    z = torch.zeros_like
+    mu, vu, mi, vi = z(pu), z(pu), z(pi), z(pi)
+    st = ops.new_adam_state(dev, history=True)
+    su, si = ops.new_row_stamps(U, st), ops.new_row_stamps(I, st)
+    hu, hi = ops.new_list_heads(U, dev), ops.new_list_heads(I, dev)
+    loss = torch.zeros(2, device=dev)
+    nu, ni = ut.copy(), it.copy()
+    nmu, nvu, nmi, nvi = (np.zeros_like(a) for a in (ut, ut, it, it))
+    zb_u, zb_i = np.zeros((U, 1), np.float32), np.zeros((I, 1), np.float32)
+    for s in range(steps):
+        hot = 30 if s % 2 == 0 else 250                     # small id ranges: many duplicates; rows come and go
+        u, i, j = (rng.integers(0, n, B).astype(np.int64) for n in (hot, hot + 20, hot + 20))
+        if loss_kind == "bce":
+            lo, gu, gi = O.plain_mf_bce_grads(nu, ni, u, i, j, l2u, l2i)
+        else:
+            lo, gu, gi, _ = O.plain_mf_bpr_grads(nu, ni, zb_u, zb_i, u, i, j)
+        O.adam_step(nu, gu, nmu, nvu, s + 1, lr); O.adam_step(ni, gi, nmi, nvi, s + 1, lr)
+        ops.plain_mf_step(pu, pi, mu, vu, mi, vi, hu, hi, T(u, dev), T(i, dev), T(j, dev), st, lr, loss,
+                          loss=ops.LOSS_BCE if loss_kind == "bce" else ops.LOSS_BPR, l2_u=l2u, l2_i=l2i,
+                          optimizer=ops.OPT_ADAM_DENSE_EXACT, stamp_user=su, stamp_item=si)
+        assert abs(loss[0].item() - float(lo)) < 1e-4 * max(1.0, abs(float(lo))), (s, loss[0].item(), float(lo))
+        assert int(hu.max()) == -1 and int(hi.max()) == -1 and int(hu.min()) == -1      # list heads re-armed
+    assert int(st[0]) == steps
+    ops.adam_flush(pu, mu, vu, su, st); ops.adam_flush(pi, mi, vi, si, st)
+    # (fp32 vs fp64 oracle runs of this scenario differ by < 1e-6: a 2e-5 bound catches a single skipped or doubled
+    # zero-gradient replay, which moves a row by ~0.6 lr)
+    assert np.abs(pu.cpu().numpy() - nu).max() < 2e-5 and np.abs(pi.cpu().numpy() - ni).max() < 2e-5
+    assert rel_err(mu.cpu().numpy(), nmu) < 1e-4 and rel_err(vi.cpu().numpy(), nvi) < 1e-4
+    untouched = np.setdiff1d(np.arange(U), np.arange(250))
+    assert np.array_equal(pu.cpu().numpy()[untouched], ut[untouched])            # rows no gradient ever reached
+
+
+def test_plain_mf_fused_step_modes(dev):
+    """(a) the fused step against the two-kernel path (sml_plain_mf_grads + dense Adam sweep); (b) when the same rows are
+    touched at every step the exact and the sparse mode are the same arithmetic: bit-identical; (c) SML_OPT_ADAM_SPARSE
+    moves only the rows of the batch."""
+    from sml_b200 import ops
+    rng = np.random.default_rng(12)
+    U, I, B = 500, 1200, 400
+    ut = (0.3 * rng.standard_normal((U, 64))).astype(np.float32); it = (0.3 * rng.standard_normal((I, 64))).astype(np.float32)
+    u = rng.permutation(U)[:B].astype(np.int64)
+    ij = rng.permutation(I)[:2 * B].astype(np.int64)
+    i, j = ij[:B].copy(), ij[B:].copy()
+    z = torch.zeros_like
+    # two-kernel path
+    pu0, pi0 = T(ut, dev), T(it, dev)
+    gu, gi, loss0 = z(pu0), z(pi0), torch.zeros(2, device=dev)
+    mu0, vu0, mi0, vi0 = z(pu0), z(pu0), z(pi0), z(pi0)
+    st0 = ops.new_adam_state(dev)
+    for _ in range(2):
+        ops.plain_mf_grads(pu0, pi0, T(u, dev), T(i, dev), T(j, dev), gu, gi, loss0, loss=ops.LOSS_BCE, l2_u=1e-3, l2_i=1e-3)
+        ops.adam_tick(st0, 0.01)
+        ops.adam_dense(pu0, mu0, vu0, gu, st0); ops.adam_dense(pi0, mi0, vi0, gi, st0)
+    got = {}
+    for mode in (ops.OPT_ADAM_DENSE_EXACT, ops.OPT_ADAM_SPARSE):
+        pu, pi, loss = T(ut, dev), T(it, dev), torch.zeros(2, device=dev)
+        mu, vu, mi, vi = z(pu), z(pu), z(pi), z(pi)
+        st = ops.new_adam_state(dev, history=True)
+        su, si = ops.new_row_stamps(U, st), ops.new_row_stamps(I, st)
+        hu, hi = ops.new_list_heads(U, dev), ops.new_list_heads(I, dev)
+        for _ in range(2):
+            ops.plain_mf_step(pu, pi, mu, vu, mi, vi, hu, hi, T(u, dev), T(i, dev), T(j, dev), st, 0.01, loss, loss=ops.LOSS_BCE,
+                              l2_u=1e-3, l2_i=1e-3, optimizer=mode, stamp_user=su, stamp_item=si)
+        if mode == ops.OPT_ADAM_DENSE_EXACT:
+            ops.adam_flush(pu, mu, vu, su, st); ops.adam_flush(pi, mi, vi, si, st)
+        # (the dot products are summed in a different lane order than in the two-kernel path: last-bit differences)
+        assert (pu - pu0).abs().max().item() < 2e-6 and (pi - pi0).abs().max().item() < 2e-6
+        assert rel_err(mu.cpu().numpy(), mu0.cpu().numpy()) < 1e-5 and rel_err(vi.cpu().numpy(), vi0.cpu().numpy()) < 1e-5
+        assert abs(loss[1].item() - loss0[1].item()) < 1e-5
+        got[mode] = (pu, pi, mu, vi)
+    for a, b in zip(got[ops.OPT_ADAM_DENSE_EXACT], got[ops.OPT_ADAM_SPARSE]):
+        assert torch.equal(a, b)
+    # sparse mode: a row touched at step 1 only does NOT move at step 2 (dense Adam would move it through its momentum)
+    pu, pi, loss = T(ut, dev), T(it, dev), torch.zeros(2, device=dev)
+    mu, vu, mi, vi = z(pu), z(pu), z(pi), z(pi)
+    st = ops.new_adam_state(dev, history=True)
+    hu, hi = ops.new_list_heads(U, dev), ops.new_list_heads(I, dev)
+    args = dict(loss=ops.LOSS_BCE, l2_u=1e-3, l2_i=1e-3, optimizer=ops.OPT_ADAM_SPARSE)
+    ops.plain_mf_step(pu, pi, mu, vu, mi, vi, hu, hi, T(u[:10], dev), T(i[:10], dev), T(j[:10], dev), st, 0.01, loss, **args)
+    snap = pu[u[:10]].clone()
+    ops.plain_mf_step(pu, pi, mu, vu, mi, vi, hu, hi, T(u[10:20], dev), T(i[10:20], dev), T(j[10:20], dev), st, 0.01, loss, **args)
+    assert torch.equal(pu[u[:10]], snap) and not torch.equal(pu[u[10:20]], T(ut, dev)[u[10:20]])
+
+
 def test_eval_sees_kernel_updates(dev):
     """The step kernels write the tables through raw pointers (no tensor version bump): a test set
     evaluated before and after a training step must not return a stale scoring pass."""
