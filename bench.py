@@ -242,6 +242,95 @@ def reference_leg(device, scale, timeout=600):
 
 
 # --------------------------------------------------------------------------------------------
+# config 4 / 5: row-sharded tables (200 M users x 20 M items at 8 GPUs), NCCL all-to-all row exchange, theta all-reduce
+# --------------------------------------------------------------------------------------------
+SHARDED = dict(users_per_gpu=25_000_000, items_per_gpu=2_500_000, batch_per_gpu=8192, steps=16, eval_pairs_per_gpu=16384)
+
+
+def sharded_leg(world, rank, dev, cfg=SHARDED):
+    """BASELINE.json configs[3] and [4] at ``world`` GPUs: every table copy sharded by row id (25 M user + 2.5 M item rows
+    per GPU = 200 M x 20 M at 8), one MF epoch, a full-table transfer (updata), one transfer epoch and a full-catalog
+    evaluation through sml_b200.shard.ShardedSML -- NCCL all-to-alls of ids / row pairs / row gradients and the theta
+    all-reduce timed with CUDA events -- and the SAME code with world = 1 on the same per-GPU shape (no collectives) as the
+    weak-scaling base.  Times are the max over ranks."""
+    import contextlib, io
+    import torch
+    import torch.distributed as dist
+    from sml_b200.model.conv_transfer import ConvTransfer_com
+    from sml_b200.shard import CommTimers, ShardedSML
+    Ul, Il, Bl, S, NP = cfg["users_per_gpu"], cfg["items_per_gpu"], cfg["batch_per_gpu"], cfg["steps"], cfg["eval_pairs_per_gpu"]
+    g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+
+    def mx(ms):
+        if world == 1:
+            return float(ms)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t)
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        return mx(e0.elapsed_time(e1))
+
+    def run(w, r, group):
+        with torch.random.fork_rng(devices=[]), contextlib.redirect_stdout(io.StringIO()):
+            torch.manual_seed(7)
+            tr = ConvTransfer_com(64, 64).to(dev)             # replicated theta: same seed on every rank
+        ut = torch.empty(Ul, 64, device=dev).normal_(0, 0.1, generator=g)
+        it = torch.empty(Il, 64, device=dev).normal_(0, 0.1, generator=g)
+        sh = ShardedSML(ut, it, tr, world=w, rank=r, group=group)
+        rnd = lambda n, hi: torch.randint(0, hi, (n,), device=dev, generator=g)
+        tri = lambda: (rnd(Bl * S, Ul * w), rnd(Bl * S, Il * w), rnd(Bl * S, Il * w))
+        out = {}
+        sh.save_last()
+        sh.mf_epoch(*tri(), Bl); sh.flush(); sh.save_hat(); sh.tr_epoch(*tri(), Bl)          # warm-up (kernel setup, NCCL channels)
+        comm = CommTimers()
+        sh.ex.comm = comm
+        a = tri()
+        ms = timed(lambda: (sh.mf_epoch(*a, Bl), sh.flush()))
+        out["mf_step_ms"] = ms / S; out["mf_triples_per_s"] = Bl * w * S / ms * 1e3
+        c_mf = comm.summary(); comm.events.clear(); comm.bytes.clear()
+        sh.save_hat()
+        out["updata_ms"] = timed(sh.updata)
+        out["updata_rows_per_s"] = (Ul + Il) * w / out["updata_ms"] * 1e3
+        out["updata_tflops_fp32_equiv"] = (Ul + Il) * w * TRANSFER_FLOP_PER_ROW / out["updata_ms"] / 1e9
+        a = tri()
+        ms = timed(lambda: sh.tr_epoch(*a, Bl))
+        out["tr_step_ms"] = ms / S; out["tr_triples_per_s"] = Bl * w * S / ms * 1e3
+        c_tr = comm.summary(); comm.events.clear(); comm.bytes.clear()
+        pairs = torch.stack([rnd(NP, Ul * w), rnd(NP, Il * w)], 1)
+        sh.eval_fullcat(pairs, 20)
+        ms = timed(lambda: sh.eval_fullcat(pairs, 20))
+        out["fullcat_ms"] = ms; out["fullcat_pairs_per_s"] = NP * w / ms * 1e3
+        out["fullcat_tflops_fp32_equiv"] = 2.0 * 64 * NP * w * Il * w / (ms * 1e-3) / 1e12
+        per_step = lambda c: {t: dict(ms_per_step=mx(v["ms"] / S), bytes_to_peers_per_step=v["bytes_to_peers"] // S, calls_per_epoch=v["calls"])
+                              for t, v in sorted(c.items())}
+        out["collectives_mf"] = per_step(c_mf) if w > 1 else {}
+        out["collectives_tr"] = per_step(c_tr) if w > 1 else {}
+        del sh, ut, it
+        torch.cuda.empty_cache()
+        return out
+
+    base = run(1, 0, None)                       # the same code at world = 1 on this GPU's shard shape
+    res = dict(config="configs[3]+[4]: row-sharded SML on synthetic tables, id % world ownership", world=world,
+               users_per_gpu=Ul, items_per_gpu=Il, total_users=Ul * world, total_items=Il * world, batch_per_gpu=Bl,
+               steps_per_epoch=S, eval_pairs_per_gpu=NP, time="CUDA events, max over ranks; exchange planning (ids all-to-all, one host "
+               "sync per epoch) inside the timed region", world1_same_shape=base)
+    if world > 1:
+        res.update(run(world, rank, None))
+        lim = {}
+        for k in ("collectives_mf", "collectives_tr"):
+            c = res[k]
+            if c:
+                t = max(c, key=lambda x: c[x]["ms_per_step"])
+                lim[k] = dict(slowest=t, ms_per_step=c[t]["ms_per_step"], nvlink_gbs=c[t]["bytes_to_peers_per_step"] / max(c[t]["ms_per_step"], 1e-9) / 1e6)
+        res["limiting_collective"] = lim
+    return res
+
+
+# --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
 def run_ours(a):
@@ -262,9 +351,18 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "INFO")              # the communicator log (ranks, NVLink / NVLS channels) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         dist.init_process_group("nccl", device_id=dev)
     lib()
     quiet = open(os.devnull, "w")
+    if a.sharded_only:
+        res = sharded_leg(world, rank, dev)
+        if rank == 0:
+            print(json.dumps({"sharded": res, "n_gpus": world}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     W, K = a.warmup, a.steps
     shape = dict(YELP)
@@ -466,6 +564,11 @@ def run_ours(a):
                              "1.965 GHz = 12.4 TB/s); k_eval_prefilter gets the identical counts from a bf16 copy of the table (128 B per "
                              "candidate) + exact fp32 re-scoring of the ~0.6 % it cannot decide, i.e. it reads about half of those bytes"},
     }
+    if not a.no_sharded:
+        del meta
+        torch.cuda.empty_cache()
+        out["sharded"] = sharded_leg(world, rank, dev)
+        meta = None
     if rank == 0:
         if world == 1 and not a.no_cpu_baseline:
             del meta
@@ -498,6 +601,8 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="rows per period (default: the Yelp shape, 75000)")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     ap.add_argument("--skip-e2e", dest="skip_e2e", action="store_true", help="profiling runs only: skip the host-buffer arm")
+    ap.add_argument("--no-sharded", dest="no_sharded", action="store_true", help="skip the row-sharded config-4/5 leg")
+    ap.add_argument("--sharded-only", dest="sharded_only", action="store_true", help="run only the row-sharded config-4/5 leg")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference_arm(a)

@@ -25,6 +25,46 @@ import torch
 import torch.distributed as dist
 
 
+class CommTimers(object):
+    """CUDA-event timers + byte counters around the collectives of the sharded path (bench.py's ``sharded`` object).
+    ``with comm("rows", nbytes_to_peers): dist.all_to_all_single(...)`` records one event pair on the current stream
+    (synchronous torch.distributed collectives make the current stream wait for NCCL's, so the pair brackets them)."""
+
+    def __init__(self):
+        self.events, self.bytes, self._tag = {}, {}, None
+
+    def __call__(self, tag, nbytes=0):
+        self._tag = tag
+        self.bytes[tag] = self.bytes.get(tag, 0) + int(nbytes)
+        return self
+
+    def __enter__(self):
+        self._e0 = torch.cuda.Event(enable_timing=True)
+        self._e0.record()
+
+    def __exit__(self, *exc):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.events.setdefault(self._tag, []).append((self._e0, e1))
+
+    def summary(self):
+        """-> {tag: dict(calls, ms, bytes_to_peers)} (synchronises)."""
+        torch.cuda.synchronize()
+        return {t: dict(calls=len(ev), ms=float(sum(a.elapsed_time(b) for a, b in ev)), bytes_to_peers=self.bytes.get(t, 0))
+                for t, ev in self.events.items()}
+
+
+class _NoTimer(object):
+    def __call__(self, *a, **k):
+        return self
+
+    def __enter__(self):
+        pass
+
+    def __exit__(self, *exc):
+        pass
+
+
 class ExchangePlan(object):
     __slots__ = ("order", "inverse", "send_counts", "recv_counts", "recv_loc", "n")
 
@@ -34,14 +74,18 @@ class RowExchange(object):
 
     def __init__(self, world, rank, group=None):
         self.world, self.rank, self.group = world, rank, group
+        self.comm = _NoTimer()               # bench.py installs a CommTimers here
 
-    def _a2a(self, send, send_counts, recv_counts):
+    def _a2a(self, send, send_counts, recv_counts, tag="ids"):
         out = send.new_empty((int(sum(recv_counts)),) + tuple(send.shape[1:]))
         if self.world == 1:
             out.copy_(send)
             return out
-        dist.all_to_all_single(out, send.contiguous(), output_split_sizes=list(recv_counts), input_split_sizes=list(send_counts),
-                               group=self.group)
+        row_bytes = send.element_size() * (send[0].numel() if send.dim() > 1 and send.shape[0] else 1)
+        to_peers = (int(sum(send_counts)) - int(send_counts[self.rank])) * row_bytes
+        with self.comm(tag, to_peers):
+            dist.all_to_all_single(out, send.contiguous(), output_split_sizes=list(recv_counts), input_split_sizes=list(send_counts),
+                                   group=self.group)
         return out
 
     def plan(self, ids):
@@ -113,13 +157,13 @@ class RowExchange(object):
     def fetch(self, plan, gather_fn):
         """gather_fn(local_rows) -> [m, W] rows of this rank's shard; returns [n, W] in the original id order."""
         mine = gather_fn(plan.recv_loc)
-        got = self._a2a(mine, plan.recv_counts, plan.send_counts)
+        got = self._a2a(mine, plan.recv_counts, plan.send_counts, tag="rows")
         return got[plan.inverse]
 
     def push(self, plan, rows, scatter_fn):
         """rows: [n, W] per-id payload (row gradients) in the original id order; scatter_fn(local_rows, payload)
         is called once on the owner side with everything this rank received."""
-        recv = self._a2a(rows[plan.order], plan.send_counts, plan.recv_counts)
+        recv = self._a2a(rows[plan.order], plan.send_counts, plan.recv_counts, tag="grads")
         scatter_fn(plan.recv_loc, recv)
 
 
@@ -273,7 +317,8 @@ class ShardedSML(object):
         if scale != 1.0:
             g.mul_(scale)
         if self.world > 1:
-            dist.all_reduce(g, group=self.group)
+            with self.ex.comm("theta", 2 * (self.world - 1) * g.numel() * 4 // self.world):    # ring all-reduce volume per rank
+                dist.all_reduce(g, group=self.group)
         ops.adam_tick(self.tr_state, self.tr_lr)
         ops.adam_dense(self.transfer.theta, self.m_theta, self.v_theta, g, self.tr_state, weight_decay=self.tr_l2)
         return self.loss[0] * scale
