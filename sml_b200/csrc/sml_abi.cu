@@ -26,6 +26,15 @@ int sml_use_tensor_cores() {
     return v;
 }
 
+int sml_use_fused_fwd() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SML_FUSED_FWD");
+        v = (e && strcmp(e, "0") == 0) ? 0 : 1;
+    }
+    return v;
+}
+
 int sml_use_pdl() {
     static int v = -1;
     if (v < 0) {

@@ -215,3 +215,12 @@ constexpr size_t SML_PK_THETA_BYTES = 3538944;
 int sml_launch_pack_theta(const float *theta, uint8_t *out, int n_nets, cudaStream_t st, int64_t *adam_state = nullptr, double lr = 0.0);
 
 int sml_launch_row_normalize(float *Y, int64_t n, cudaStream_t st);
+
+// fused transfer forward (umma_fused_fwd.cu): one persistent kernel for conv -> fc1 -> GELU -> fc2 over a stream of rows.
+// wpk = the net's W1 / W2 packed by sml_launch_pack_fused (sml_fused_fwd_packed_bytes() bytes).
+size_t sml_fused_fwd_packed_bytes();
+int sml_launch_pack_fused(const float *theta_net, uint8_t *out, cudaStream_t st);
+int sml_launch_transfer_fused(const float *x_t, const float *x_hat, const int64_t *ids, int64_t n_rows, int64_t pitch, int variant,
+                              const float *theta_net, const uint8_t *wpk, int normalize_out, float *out, cudaStream_t st);
+// 1 = sml_transfer_fwd uses the fused kernel (default); SML_FUSED_FWD=0 or sml_debug_set_mask(2048) select the three-kernel path
+int sml_use_fused_fwd();

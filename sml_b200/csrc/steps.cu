@@ -377,6 +377,14 @@ int sml_transfer_fwd(const float *x_t, const float *x_hat, const int64_t *ids, i
     uint8_t *Apk = (uint8_t *)take((size_t)(ch / 128) * 10 * pk_block_bytes(128));
     uint8_t *Gpk = (uint8_t *)take((size_t)(ch / 128) * 16 * pk_block_bytes(128));
     uint8_t *theta_pk = (uint8_t *)take(SML_PK_THETA_BYTES);
+    if (tc && sml_use_fused_fwd() && !(sml_debug_mask() & 2048)) {
+        // one persistent kernel over all rows: conv -> fc1 -> GELU -> fc2 (+ normalisation), nothing but the two source rows and
+        // the result row crosses HBM (umma_fused_fwd.cu); the packed weights (1.5 MB) reuse the theta_pk scratch
+        static_assert(SML_PK_THETA_BYTES >= 1572864, "fused weights must fit the packed-theta scratch");
+        rc = sml_launch_pack_fused(theta_net, theta_pk, st);
+        if (rc) return rc;
+        return sml_launch_transfer_fused(x_t, x_hat, ids, n_rows, SML_D, variant, theta_net, theta_pk, normalize_out, out, st);
+    }
     if (tc) {
         rc = sml_launch_pack_theta(theta_net, theta_pk, 1, st);
         if (rc) return rc;
