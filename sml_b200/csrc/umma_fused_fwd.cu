@@ -53,8 +53,24 @@ struct ConvW {
     float b2[5];
 };
 
-__device__ __forceinline__ uint64_t ff_desc(uint32_t saddr, uint32_t sbo) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(FF_LBO >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+// Shared-memory matrix descriptor (K-major, no swizzle, version 1) as two 32-bit halves: lo = start address >> 4 | LBO >> 4 << 16,
+// hi = SBO >> 4 | 1 << 14.  The MMA warp keeps them in uniform registers and only ever adds a constant to lo (addresses stay
+// below 2^18, so nothing carries into the LBO field).
+__device__ __forceinline__ uint32_t ff_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFF) | ((FF_LBO >> 4) << 16); }
+__host__ __device__ constexpr uint32_t ff_desc_hi(uint32_t sbo) { return (sbo >> 4) | (1u << 14); }
+__device__ __forceinline__ void ff_mma(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ bool ff_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 
 template <int R>
@@ -139,60 +155,71 @@ k_transfer_fused(FusedParams P) {
             }
         }
     } else if (warp == 9) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t ID128 = idesc_tf32(128), ID64 = idesc_tf32(64);
-            uint32_t bitem = 0, acons[2] = {0, 0}, it = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                if (it > 0) { mbar_wait(tmem_free, (it - 1) & 1); tc_fence_after(); }     // the previous tile's Y has been read
-                // ---- fc1: Z1[128 x 512] += A chunk (40 K) x W1 sub-block, 8 chunks x 4 sub-blocks ----
-                for (int c = 0; c < 8; ++c) {
-                    const int s = c & 1;
-                    mbar_wait(&a_full[s], acons[s] & 1); ++acons[s];
-                    tc_fence_after();
-                    const uint32_t a_hi = smem_u32(sA + s * FF_SLOT), a_lo = a_hi + FF_HALF_A;
-                    for (int nb = 0; nb < 4; ++nb, ++bitem) {
-                        const uint32_t bs = bitem % FF_NB;
-                        mbar_wait(&b_full[bs], (bitem / FF_NB) & 1);
-                        tc_fence_after();
-                        const uint32_t b_hi = smem_u32(sB + bs * FF_SLOT), b_lo = b_hi + FF_HALF_A;
-                        const uint32_t d = tmem + nb * 128;
+        // ===== MMA issuer: the whole warp runs the loops (warp-uniform control flow keeps the descriptors in uniform registers),
+        // one elected lane issues the tcgen05 instructions =====
+        constexpr uint32_t ID128 = idesc_tf32(128), ID64 = idesc_tf32(64);
+        constexpr uint32_t HI_A = ff_desc_hi(FF_SBO_A), HI_G = ff_desc_hi(FF_SBO_G);
+        constexpr uint32_t KSTEP = (2 * FF_LBO) >> 4;                  // descriptor-lo increment per K step of 8
+        const bool leader = ff_elect_one();
+        uint32_t bitem = 0, acons0 = 0, acons1 = 0, it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            if (it > 0) { mbar_wait(tmem_free, (it - 1) & 1); tc_fence_after(); }         // the previous tile's Y has been read
+            // ---- fc1: Z1[128 x 512] += A chunk (40 K) x W1 sub-block, 8 chunks x 4 sub-blocks ----
+#pragma unroll 1
+            for (int c = 0; c < 8; ++c) {
+                const int s = c & 1;
+                if (s == 0) { mbar_wait(&a_full[0], acons0 & 1); ++acons0; } else { mbar_wait(&a_full[1], acons1 & 1); ++acons1; }
+                tc_fence_after();
+                const uint32_t a_hi = ff_desc_lo(smem_u32(sA + s * FF_SLOT)), a_lo = ff_desc_lo(smem_u32(sA + s * FF_SLOT) + FF_HALF_A);
 #pragma unroll
-                        for (int k = 0; k < 5; ++k) {
-                            const uint32_t ko = k * 2 * FF_LBO;
-                            umma_tf32(d, ff_desc(a_lo + ko, FF_SBO_A), ff_desc(b_hi + ko, FF_SBO_A), ID128, (c | k) != 0);
-                            umma_tf32(d, ff_desc(a_hi + ko, FF_SBO_A), ff_desc(b_lo + ko, FF_SBO_A), ID128, 1);
-                            umma_tf32(d, ff_desc(a_hi + ko, FF_SBO_A), ff_desc(b_hi + ko, FF_SBO_A), ID128, 1);
-                        }
-                        umma_commit(&b_empty[bs]);
-                    }
-                    umma_commit(&a_empty[s]);
-                }
-                umma_commit(z_full);
-                // ---- fc2: Y_{c2/4}[128 x 64] += GELU(Z1) chunk (32 K) x W2 chunk; Y_a overlaps Z1 columns 0..63 ----
-                for (int c2 = 0; c2 < 16; ++c2, ++bitem) {
-                    const int s = c2 & 1;
-                    mbar_wait(&a_full[s], acons[s] & 1); ++acons[s];
-                    if (c2 == 0) mbar_wait(&a_full[1], acons[1] & 1);       // chunk 1 published => Z1 columns 32..63 have been read too
-                    tc_fence_after();
+                for (int nb = 0; nb < 4; ++nb, ++bitem) {
                     const uint32_t bs = bitem % FF_NB;
                     mbar_wait(&b_full[bs], (bitem / FF_NB) & 1);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(sA + s * FF_SLOT), a_lo = a_hi + FF_HALF_G;
-                    const uint32_t b_hi = smem_u32(sB + bs * FF_SLOT), b_lo = b_hi + FF_HALF_W2;
-                    const uint32_t d = tmem + (uint32_t)(c2 >> 2) * 64;
+                    const uint32_t b_hi = ff_desc_lo(smem_u32(sB + bs * FF_SLOT)), b_lo = ff_desc_lo(smem_u32(sB + bs * FF_SLOT) + FF_HALF_A);
+                    const uint32_t d = tmem + nb * 128;
+                    if (leader) {
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) {
+                            ff_mma(d, a_lo + k * KSTEP, b_hi + k * KSTEP, HI_A, ID128, (c | k) != 0);
+                            ff_mma(d, a_hi + k * KSTEP, b_lo + k * KSTEP, HI_A, ID128, 1);
+                            ff_mma(d, a_hi + k * KSTEP, b_hi + k * KSTEP, HI_A, ID128, 1);
+                        }
+                        umma_commit(&b_empty[bs]);
+                    }
+                    __syncwarp();
+                }
+                if (leader) umma_commit(&a_empty[s]);
+                __syncwarp();
+            }
+            if (leader) umma_commit(z_full);
+            __syncwarp();
+            // ---- fc2: Y_{c2/4}[128 x 64] += GELU(Z1) chunk (32 K) x W2 chunk; Y_a overlaps Z1 columns 0..63 ----
+#pragma unroll 1
+            for (int c2 = 0; c2 < 16; ++c2, ++bitem) {
+                const int s = c2 & 1;
+                if (s == 0) { mbar_wait(&a_full[0], acons0 & 1); ++acons0; } else { mbar_wait(&a_full[1], acons1 & 1); ++acons1; }
+                if (c2 == 0) mbar_wait(&a_full[1], acons1 & 1);           // chunk 1 published => Z1 columns 32..63 have been read too
+                const uint32_t bs = bitem % FF_NB;
+                mbar_wait(&b_full[bs], (bitem / FF_NB) & 1);
+                tc_fence_after();
+                const uint32_t a_hi = ff_desc_lo(smem_u32(sA + s * FF_SLOT)), a_lo = ff_desc_lo(smem_u32(sA + s * FF_SLOT) + FF_HALF_G);
+                const uint32_t b_hi = ff_desc_lo(smem_u32(sB + bs * FF_SLOT)), b_lo = ff_desc_lo(smem_u32(sB + bs * FF_SLOT) + FF_HALF_W2);
+                const uint32_t d = tmem + (uint32_t)(c2 >> 2) * 64;
+                if (leader) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const uint32_t ko = k * 2 * FF_LBO;
-                        umma_tf32(d, ff_desc(a_lo + ko, FF_SBO_G), ff_desc(b_hi + ko, FF_SBO_G), ID64, ((c2 & 3) | k) != 0);
-                        umma_tf32(d, ff_desc(a_hi + ko, FF_SBO_G), ff_desc(b_lo + ko, FF_SBO_G), ID64, 1);
-                        umma_tf32(d, ff_desc(a_hi + ko, FF_SBO_G), ff_desc(b_hi + ko, FF_SBO_G), ID64, 1);
+                        ff_mma(d, a_lo + k * KSTEP, b_hi + k * KSTEP, HI_G, ID64, ((c2 & 3) | k) != 0);
+                        ff_mma(d, a_hi + k * KSTEP, b_lo + k * KSTEP, HI_G, ID64, 1);
+                        ff_mma(d, a_hi + k * KSTEP, b_hi + k * KSTEP, HI_G, ID64, 1);
                     }
                     umma_commit(&b_empty[bs]);
                     umma_commit(&a_empty[s]);
                 }
-                umma_commit(y_full);
+                __syncwarp();
             }
+            if (leader) umma_commit(y_full);
+            __syncwarp();
         }
     } else {
         // ===== compute warps: conv stage (fc1 phase), GELU + re-split (drain phase), final epilogue =====
