@@ -70,30 +70,34 @@ k_fullcat_rank(const uint8_t *__restrict__ Upk, const uint8_t *__restrict__ Ipk,
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t IDESC = idesc_tf32(128);
-            mbar_wait(a_full, 0);
-            for (int j = 0; j < ntiles; ++j) {
-                const int s = j % FC_STAGES, acc = j & 1;
-                mbar_wait(&b_full[s], (j / FC_STAGES) & 1);
-                if (j >= 2) mbar_wait(&acc_empty[acc], ((j >> 1) - 1) & 1);          // epilogue drained this accumulator
-                tc_fence_after();
-                const uint32_t d = tmem + acc * 128;
+        // the whole warp runs the loop (descriptors in uniform registers), one elected lane issues
+        constexpr uint32_t IDESC = idesc_tf32(128);
+        constexpr uint32_t DHI = desc_hi(PK_SBO), KSTEP = (2 * PK_LBO) >> 4;
+        const bool leader = elect_one();
+        mbar_wait(a_full, 0);
+        for (int j = 0; j < ntiles; ++j) {
+            const int s = j % FC_STAGES, acc = j & 1;
+            mbar_wait(&b_full[s], (j / FC_STAGES) & 1);
+            if (j >= 2) mbar_wait(&acc_empty[acc], ((j >> 1) - 1) & 1);          // epilogue drained this accumulator
+            tc_fence_after();
+            const uint32_t d = tmem + acc * 128;
+            if (leader) {
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
-                    const uint32_t a_hi = smem_u32(sA) + c * pk_block_bytes(128), a_lo = a_hi + pk_half_bytes(128);
-                    const uint32_t b_hi = smem_u32(sB + s * FC_TILE_BYTES) + c * pk_block_bytes(128), b_lo = b_hi + pk_half_bytes(128);
+                    const uint32_t a_hi = desc_lo(smem_u32(sA) + c * pk_block_bytes(128), PK_LBO), a_lo = desc_lo(smem_u32(sA) + c * pk_block_bytes(128) + pk_half_bytes(128), PK_LBO);
+                    const uint32_t b_hi = desc_lo(smem_u32(sB + s * FC_TILE_BYTES) + c * pk_block_bytes(128), PK_LBO),
+                                   b_lo = desc_lo(smem_u32(sB + s * FC_TILE_BYTES) + c * pk_block_bytes(128) + pk_half_bytes(128), PK_LBO);
 #pragma unroll
                     for (int k = 0; k < PK_BK / 8; ++k) {
-                        const uint32_t ko = k * 2 * PK_LBO;
-                        umma_tf32(d, make_desc(a_lo + ko), make_desc(b_hi + ko), IDESC, (c | k) != 0);
-                        umma_tf32(d, make_desc(a_hi + ko), make_desc(b_lo + ko), IDESC, 1);
-                        umma_tf32(d, make_desc(a_hi + ko), make_desc(b_hi + ko), IDESC, 1);
+                        umma_tf32_h(d, a_lo + k * KSTEP, b_hi + k * KSTEP, DHI, IDESC, (c | k) != 0);
+                        umma_tf32_h(d, a_hi + k * KSTEP, b_lo + k * KSTEP, DHI, IDESC, 1);
+                        umma_tf32_h(d, a_hi + k * KSTEP, b_hi + k * KSTEP, DHI, IDESC, 1);
                     }
                 }
                 umma_commit(&b_empty[s]);
                 umma_commit(&acc_full[acc]);
             }
+            __syncwarp();
         }
     } else {
         const int quarter = warp & 3, chalf = (warp - 2) >> 2;

@@ -53,25 +53,12 @@ struct ConvW {
     float b2[5];
 };
 
-// Shared-memory matrix descriptor (K-major, no swizzle, version 1) as two 32-bit halves: lo = start address >> 4 | LBO >> 4 << 16,
-// hi = SBO >> 4 | 1 << 14.  The MMA warp keeps them in uniform registers and only ever adds a constant to lo (addresses stay
-// below 2^18, so nothing carries into the LBO field).
-__device__ __forceinline__ uint32_t ff_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFF) | ((FF_LBO >> 4) << 16); }
-__host__ __device__ constexpr uint32_t ff_desc_hi(uint32_t sbo) { return (sbo >> 4) | (1u << 14); }
-__device__ __forceinline__ void ff_mma(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "setp.ne.b32 p, %5, 0;\n\t"
-        "mov.b64 da, {%1, %3};\n\t"
-        "mov.b64 db, {%2, %3};\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
-        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+__device__ __forceinline__ uint32_t ff_desc_lo(uint32_t saddr) { return desc_lo(saddr, FF_LBO); }
+__host__ __device__ constexpr uint32_t ff_desc_hi(uint32_t sbo) { return desc_hi(sbo); }
+__device__ __forceinline__ void ff_mma(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t d_hi, uint32_t idesc, uint32_t acc) {
+    umma_tf32_h(d, a_lo, b_lo, d_hi, idesc, acc);
 }
-__device__ __forceinline__ bool ff_elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
+__device__ __forceinline__ bool ff_elect_one() { return elect_one(); }
 
 template <int R>
 __device__ __forceinline__ void conv_point(const ConvW &w, float x0, float x1, float x2, float (&out)[5]) {

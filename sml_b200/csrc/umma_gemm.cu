@@ -81,6 +81,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+__device__ __forceinline__ void umma_tf32_h(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t d_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(d_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -231,29 +240,33 @@ k_umma_gemm(UmmaParams P) {
     const int nchunks = (p.K + UM_BK - 1) / UM_BK;
 
     if (warp == MMA_WARP) {
-        // ===== MMA issuer: one thread; waits for a full stage, issues its 12 MMAs, commits to empty[s] =====
-        if ((threadIdx.x & 31) == 0) {
-            for (int c = 0; c < nchunks; ++c) {
-                const int s = c % UM_STAGES;
-                mbar_wait(&full[s], (c / UM_STAGES) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_hi = smem_u32(smem + s * S::STAGE), a_lo = a_hi + S::A_BYTES, b_hi = a_hi + 2 * S::A_BYTES,
-                               b_lo = b_hi + S::B_BYTES;
+        // ===== MMA issuer: the whole warp runs the loop (warp-uniform: descriptors stay in uniform registers), one elected
+        // lane waits-for-full / issues the 12 MMAs of a stage / commits to empty[s] =====
+        constexpr uint32_t DHI = (UM_SBO >> 4) | (1u << 14), KSTEP = (2 * UM_LBO) >> 4;
+        uint32_t leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+        auto dlo = [](uint32_t a) { return ((a >> 4) & 0x3FFF) | ((UM_LBO >> 4) << 16); };
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % UM_STAGES;
+            mbar_wait(&full[s], (c / UM_STAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = smem_u32(smem + s * S::STAGE);
+            const uint32_t a_hi = dlo(sa), a_lo = dlo(sa + S::A_BYTES), b_hi = dlo(sa + 2 * S::A_BYTES), b_lo = dlo(sa + 2 * S::A_BYTES + S::B_BYTES);
+            // K chunks alternate over UM_NACC accumulators (see umma_packed.cu: the tensor core's fp32 adder
+            // truncates, so short accumulation chains summed in the epilogue are more accurate)
+            const uint32_t d = tmem + (uint32_t)(c % UM_NACC) * BN;
+            if (leader) {
 #pragma unroll
-                for (int k = 0; k < UM_BK / 8; ++k) {
-                    const uint32_t ko = k * 2 * UM_LBO;                          // one MMA = K 8 = two core matrices
-                    const uint64_t ah = make_desc(a_hi + ko), al = make_desc(a_lo + ko), bh = make_desc(b_hi + ko), bl = make_desc(b_lo + ko);
-                    // K chunks alternate over UM_NACC accumulators (see umma_packed.cu: the tensor core's fp32 adder
-                    // truncates, so short accumulation chains summed in the epilogue are more accurate)
-                    const uint32_t d = tmem + (uint32_t)(c % UM_NACC) * BN;
-                    umma_tf32(d, al, bh, IDESC, (c >= UM_NACC) || (k != 0));     // small terms first; first MMA overwrites
-                    umma_tf32(d, ah, bl, IDESC, 1);
-                    umma_tf32(d, ah, bh, IDESC, 1);
+                for (int k = 0; k < UM_BK / 8; ++k) {                            // one MMA = K 8 = two core matrices
+                    umma_tf32_h(d, a_lo + k * KSTEP, b_hi + k * KSTEP, DHI, IDESC, (c >= UM_NACC) || (k != 0));   // small terms first; first MMA overwrites
+                    umma_tf32_h(d, a_hi + k * KSTEP, b_lo + k * KSTEP, DHI, IDESC, 1);
+                    umma_tf32_h(d, a_hi + k * KSTEP, b_hi + k * KSTEP, DHI, IDESC, 1);
                 }
                 umma_commit(&empty[s]);                                          // stage reusable once these MMAs retire
             }
-            umma_commit(done);
+            __syncwarp();
         }
+        if (leader) umma_commit(done);
         __syncwarp();
     } else {
         // ===== producers: global fp32 -> registers (two chunks in flight) -> hi/lo split -> canonical smem =====

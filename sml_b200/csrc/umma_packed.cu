@@ -65,6 +65,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_tf32_h(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t d_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(d_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -152,27 +161,34 @@ k_umma_packed(PkParams P) {
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            for (int c = 0; c < c_end - c_beg; ++c) {
-                const int s = c % PKG_STAGES;
-                mbar_wait(&full[s], (c / PKG_STAGES) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_hi = smem_u32(smem + s * S::STAGE), a_lo = a_hi + pk_half_bytes(128);
-                const uint32_t b_hi = a_hi + S::A_BYTES, b_lo = b_hi + pk_half_bytes(BN);
+        // the whole warp runs the loop (warp-uniform control flow keeps the descriptors in uniform registers), one elected lane
+        // issues: ~3 instructions per tcgen05.mma instead of ~16
+        constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t DHI = (PK_SBO >> 4) | (1u << 14), KSTEP = (2 * PK_LBO) >> 4;
+        uint32_t leader;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+        for (int c = 0; c < c_end - c_beg; ++c) {
+            const int s = c % PKG_STAGES;
+            mbar_wait(&full[s], (c / PKG_STAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = smem_u32(smem + s * S::STAGE);
+            const uint32_t a_hi = ((sa >> 4) & 0x3FFF) | ((PK_LBO >> 4) << 16), a_lo = (((sa + pk_half_bytes(128)) >> 4) & 0x3FFF) | ((PK_LBO >> 4) << 16);
+            const uint32_t b_hi = (((sa + S::A_BYTES) >> 4) & 0x3FFF) | ((PK_LBO >> 4) << 16),
+                           b_lo = (((sa + S::A_BYTES + pk_half_bytes(BN)) >> 4) & 0x3FFF) | ((PK_LBO >> 4) << 16);
+            const uint32_t d = tmem + (uint32_t)(c % PKG_NACC) * BN;               // accumulator of this chunk
+            if (leader) {
 #pragma unroll
                 for (int k = 0; k < PK_BK / 8; ++k) {
-                    const uint32_t ko = k * 2 * PK_LBO;
-                    const uint64_t ah = make_desc(a_hi + ko), al = make_desc(a_lo + ko), bh = make_desc(b_hi + ko), bl = make_desc(b_lo + ko);
-                    const uint32_t d = tmem + (uint32_t)(c % PKG_NACC) * BN;       // accumulator of this chunk
-                    umma_tf32(d, al, bh, IDESC, (c >= PKG_NACC) || (k != 0));      // its first MMA overwrites
-                    umma_tf32(d, ah, bl, IDESC, 1);
-                    umma_tf32(d, ah, bh, IDESC, 1);
+                    umma_tf32_h(d, a_lo + k * KSTEP, b_hi + k * KSTEP, DHI, IDESC, (c >= PKG_NACC) || (k != 0));   // its first MMA overwrites
+                    umma_tf32_h(d, a_hi + k * KSTEP, b_lo + k * KSTEP, DHI, IDESC, 1);
+                    umma_tf32_h(d, a_hi + k * KSTEP, b_hi + k * KSTEP, DHI, IDESC, 1);
                 }
                 umma_commit(&empty[s]);
             }
-            umma_commit(done);
+            __syncwarp();
         }
+        if (leader) umma_commit(done);
+        __syncwarp();
     } else {
         // ===== epilogue warps: straight from TMEM registers, one accumulator row per thread =====
         mbar_wait(done, 0);
