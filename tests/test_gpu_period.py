@@ -65,7 +65,11 @@ def test_period_run_matches_reference(golden, tmp_path, name, stop, replay):
     loose = 3e-3 if not name.endswith("news") else 5e-2
     scale = np.abs(g["final_user"]).max()
     assert np.abs(fu - g["final_user"]).max() < loose * scale, np.abs(fu - g["final_user"]).max()
-    assert np.abs(fi - g["final_item"]).max() < 20 * loose * np.abs(g["final_item"]).max()
+    # end-of-stream item table, element-wise relative to its scale: measured 0.5e-4 .. 2.5e-4 (Yelp-like, 3 periods of drift),
+    # 1.1e-5 .. 1.4e-5 (transfer frozen) and 1.1e-2 .. 1.3e-2 (news-like: 2 + 2 epochs on a churning item set amplify ~10x per
+    # period) over repeated runs; the bounds sit ~4x above
+    item_tol = {"period_run": 1e-3, "period_run_stop": 1e-4, "period_run_news": 5e-2}[name]
+    assert np.abs(fi - g["final_item"]).max() < item_tol * np.abs(g["final_item"]).max()
     assert np.abs(meta.user_weight_hat.cpu().numpy() - g["final_user_hat"]).max() < loose * max(1.0, np.abs(g["final_user_hat"]).max())
     for net in ("user", "item"):
         mod = getattr(meta.transfer, net + "_transfer")
