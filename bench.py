@@ -242,6 +242,76 @@ def reference_leg(device, scale, timeout=600):
 
 
 # --------------------------------------------------------------------------------------------
+# kernels in isolation, at sizes that stream from HBM (N = 1 only)
+# --------------------------------------------------------------------------------------------
+FUSED_FWD_NCU_DRAM_BYTES_PER_ROW = 741.4     # (dram__bytes_read.sum + dram__bytes_write.sum) / rows of k_transfer_fused, ncu --set full at 1 M rows (profiles/r02_kernels_ncu.md)
+PLAIN_MF_NCU_DRAM_BYTES_PER_TRIPLE = 4780.0  # same for k_plain_mf_step at 65 536 triples per step on 20 M-row tables
+
+
+def kernel_leg(dev, peaks):
+    """Per-kernel CUDA-event timings against the roofline that bounds each kernel:
+    k_transfer_fused (tensor), k_plain_mf_step (HBM; north_star kernel 1), k_fullcat_rank at config 5's 20 M items (tensor)."""
+    import torch
+    from sml_b200 import ops
+    from sml_b200.model.conv_transfer import ConvTransfer_com
+    import contextlib, io
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import plain_mf_bench
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    tf32x3_burst = float(peaks.get("bf16_tflops", 1590.0)) / 2.0 / 3.0
+    tf32x3_sust = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0 / 3.0
+    out = {}
+
+    def timed(fn, reps):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    with torch.random.fork_rng(devices=[]), contextlib.redirect_stdout(io.StringIO()):
+        tr = ConvTransfer_com(64, 64).to(dev)
+    # fused transfer forward, 4 M rows (3 GB of rows: nothing stays in L2 between launches)
+    n = 4_000_000
+    a, b, o = torch.randn(n, 64, device=dev), torch.randn(n, 64, device=dev), torch.empty(n, 64, device=dev)
+    ms = timed(lambda: ops.transfer_forward(a, b, tr.theta[:ops.NET_STRIDE], out=o), 5)
+    tf = n * TRANSFER_FLOP_PER_ROW / ms / 1e9
+    out["k_transfer_fused"] = dict(rows=n, ms=ms, rows_per_s=n / ms * 1e3, bound="tensor", achieved=tf, unit="TFLOP/s fp32-equivalent (3xTF32)",
+                                   peak=tf32x3_sust, frac=tf / tf32x3_sust, frac_of_burst_peak=tf / tf32x3_burst,
+                                   peak_note="measured cuBLAS bf16 TFLOP/s / 2 (tf32) / 3 (three MMAs per fp32 product); sustained figure: the kernel runs for milliseconds under the power cap",
+                                   hbm_gbs=n * TRANSFER_BYTES_PER_ROW / ms / 1e6, algorithmic_bytes_per_row=TRANSFER_BYTES_PER_ROW,
+                                   traffic_bytes_per_row=FUSED_FWD_NCU_DRAM_BYTES_PER_ROW)
+    del a, b, o
+    torch.cuda.empty_cache()
+    # fused plain-MF step on 20 M-row tables
+    pm = {}
+    for mode, batch in (("sparse", 262144), ("sparse", 65536), ("exact", 65536)):
+        r = plain_mf_bench.run(20_000_000, batch, 20, mode, "bpr", dev=dev)
+        pm["%s_%d" % (mode, batch)] = dict(ms=r["ms_per_step"], triples_per_s=r["triples_per_s"], achieved_gbs=r["achieved_gbs"], frac=r["frac"])
+        torch.cuda.empty_cache()
+    best = pm["sparse_262144"]
+    out["k_plain_mf_step"] = dict(rows_per_table=20_000_000, bound="hbm", achieved=best["achieved_gbs"], unit="GB/s", peak=hbm, frac=best["frac"],
+                                  algorithmic_bytes_per_triple=plain_mf_bench.BYTES_PER_TRIPLE, traffic_bytes_per_triple=PLAIN_MF_NCU_DRAM_BYTES_PER_TRIPLE,
+                                  triples_per_s=best["triples_per_s"], runs=pm,
+                                  note="BPR triples/s x 4 632 B (read + write p, m, v of 3 rows + ids) against the measured HBM copy bandwidth; uniform ids on "
+                                       "2 x 20 M-row tables (nothing fits L2); 'sparse' = Adam on the batch rows only, 'exact' = the reference's dense Adam, row-lazy")
+    # full-catalog evaluation at config 5's catalog size on one GPU: 16 384 (user, positive) pairs x 20 M items
+    n_items, n_pairs = 20_000_000, 16384
+    it = torch.randn(n_items, 64, device=dev); ut = torch.randn(65536, 64, device=dev)
+    users = torch.randint(0, 65536, (n_pairs,), device=dev); pos = torch.randint(0, n_items, (n_pairs,), device=dev)
+    ipk = ops.pack_rows(it)
+    ms = timed(lambda: ops.fullcat_ranks(ut, it, users, pos, items_packed=ipk, n_items=n_items), 2)
+    tf = 2.0 * 64 * n_pairs * n_items / ms / 1e9
+    out["k_fullcat_rank"] = dict(items=n_items, pairs=n_pairs, ms=ms, scores_per_s=n_pairs * n_items / ms * 1e3, bound="tensor", achieved=tf,
+                                 unit="TFLOP/s fp32-equivalent (3xTF32)", peak=tf32x3_sust, frac=tf / tf32x3_sust,
+                                 note="K = 64: two K chunks per 128 x 128 tile, the compare-and-count epilogue and the item-tile stream bound it, not the MMAs")
+    del it, ut, ipk
+    torch.cuda.empty_cache()
+    return out
+
+
+# --------------------------------------------------------------------------------------------
 # config 4 / 5: row-sharded tables (200 M users x 20 M items at 8 GPUs), NCCL all-to-all row exchange, theta all-reduce
 # --------------------------------------------------------------------------------------------
 SHARDED = dict(users_per_gpu=25_000_000, items_per_gpu=2_500_000, batch_per_gpu=8192, steps=16, eval_pairs_per_gpu=16384)
@@ -553,22 +623,26 @@ def run_ours(a):
         "phase_counts_per_period": {k: v[0] / K for k, v in phases.items()},
         "kernels": kern,
         "roofline_phases": roofline_phases,
-        "roofline": {"kernel": "k_eval_prefilter" if ops.EVAL_PREFILTER else "k_eval_candidates", "bound": "hbm", "achieved": ach,
-                     "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                     "traffic": ((EVAL_NCU_DRAM_BYTES_PREFILTER if ops.EVAL_PREFILTER else EVAL_NCU_DRAM_BYTES)
-                                 if shape["rows"] == 75000 else None),
-                     "peak_source": peak_src,
-                     "note": "algorithmic bytes = 264264 B x rows per launch (19.8 GB, SURVEY 8d: fp32 rows); the 31 MB item table is L2 "
-                             "resident (ncu: L2 hit 95%, DRAM traffic 0.66 GB per launch = the 600 MB id file + tables, "
-                             "profiles/r01_kernels_ncu.md), so frac exceeds 1.  The fp32 kernel runs at the L2->SM limit (~6300 B/clk x "
-                             "1.965 GHz = 12.4 TB/s); k_eval_prefilter gets the identical counts from a bf16 copy of the table (128 B per "
-                             "candidate) + exact fp32 re-scoring of the ~0.6 % it cannot decide, i.e. it reads about half of those bytes"},
+        "roofline": dict(
+            roofline_phases["tr_epoch"], kernel="transfer step = sml_tr_step: k_conv_fwd, k_umma_packed x4 (fc1, fc2, d2, d1: the tcgen05 3xTF32 GEMM), "
+            "k_loss, k_umma_gemm x2 (weight gradients), k_conv_bwd, k_adam_dense -- %d launches of this chain per period, %.0f %% of the period's "
+            "device time" % (tr_steps, 100.0 * ph_ms.get("tr_epoch", 0.0) / max(dev_s / K * 1e3, 1e-9)),
+            traffic=None, peak_source="measured cuBLAS bf16 TFLOP/s (MEASURED_PEAKS.json, burst) / 2 (tf32) / 3 (3xTF32)",
+            note="achieved = 3 x 403 456 FLOP (forward, data gradient, weight gradient) x 768 rows per step / the step's device time, measured "
+                 "live (CUDA events around every transfer epoch of the timed region).  A 768-row step is 11 dependent kernels of 4-10 us: "
+                 "latency-bound, far below the tensor roofline; the same GEMM pipeline streaming rows (kernels.k_transfer_fused, the "
+                 "updata kernel) reaches kernels.k_transfer_fused.frac of it.  Rooflines of the other phases: roofline_phases; of the "
+                 "kernels in isolation: kernels.*"),
     }
-    if not a.no_sharded:
+    if world == 1 and not a.no_kernels:
         del meta
+        meta = None
+        torch.cuda.empty_cache()
+        out["kernels"].update(kernel_leg(dev, peaks))
+    if not a.no_sharded:
+        meta = None
         torch.cuda.empty_cache()
         out["sharded"] = sharded_leg(world, rank, dev)
-        meta = None
     if rank == 0:
         if world == 1 and not a.no_cpu_baseline:
             del meta
@@ -602,6 +676,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     ap.add_argument("--skip-e2e", dest="skip_e2e", action="store_true", help="profiling runs only: skip the host-buffer arm")
     ap.add_argument("--no-sharded", dest="no_sharded", action="store_true", help="skip the row-sharded config-4/5 leg")
+    ap.add_argument("--no-kernels", dest="no_kernels", action="store_true", help="skip the isolated-kernel leg")
     ap.add_argument("--sharded-only", dest="sharded_only", action="store_true", help="run only the row-sharded config-4/5 leg")
     a = ap.parse_args()
     if a.impl == "reference":

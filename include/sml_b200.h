@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SML_ABI_VERSION 2
+#define SML_ABI_VERSION 3
 
 #define SML_OK 0
 #define SML_E_BADARG (-1)
@@ -140,6 +140,11 @@ int sml_adam_tick(int64_t *state, double lr, double beta1, double beta2, void *s
  * model/transfer.py:464-465,702). */
 int sml_adam_dense(float *p, float *m, float *v, float *g, int64_t n, const int64_t *state, double beta1, double beta2,
                    double eps, double weight_decay, int zero_grad, void *stream);
+/* The same update with the gradient first scaled by min(1, max_norm / (sqrt(*sumsq) + 1e-6)) (clip_grad_norm_);
+ * sml_sumsq writes sum(g^2) over n floats into *sumsq with a fixed summation order (scratch: 1024 floats + 1 uint). */
+int sml_sumsq(const float *g, int64_t n, float *sumsq, void *scratch, void *stream);
+int sml_adam_dense_clipped(float *p, float *m, float *v, float *g, int64_t n, const int64_t *state, double beta1, double beta2,
+                           double eps, double weight_decay, int zero_grad, const float *sumsq, double max_norm, void *stream);
 
 /* Row-lazy, bit-identical form of the dense update for embedding tables ([n_rows, 64], weight_decay 0).
  * The reference's MF optimizer is DENSE Adam over whole nn.Embedding tables (model/MF.py:21-24,
@@ -193,6 +198,14 @@ typedef struct {
      * selects the row-lazy exact Adam (sml_adam_rows) instead of the dense sweeps: sml_mf_epoch flushes both
      * tables before it returns, after sml_mf_step the caller must (sml_adam_flush) before reading the tables. */
     int32_t *stamp_user, *stamp_item;
+    /* Options that are off by default in the reference (0 = off).
+     * adaptive_beta (MF step, --need_adaptive, model/transfer.py:490-499, beta = 0.1 there): adds
+     *     sum over the distinct users u of the batch of beta * count_u / ||w_u||.detach() * ||w_u||^2
+     *   to the loss, i.e. beta * ||w_u|| per occurrence and 2 * beta * w_u / ||w_u|| to the row gradient per occurrence.
+     * clip_max_norm (transfer step, --clip_grad / --maxnorm_grad, model/transfer.py:723-727): the theta gradient is scaled
+     *   by min(1, max_norm / (||g||_2 + 1e-6)) before the Adam update (torch.nn.utils.clip_grad_norm_).  The same call in
+     *   the MF step (:507-510) clips gradients that no optimizer ever applies: nothing to do there. */
+    double adaptive_beta, clip_max_norm;
 } sml_step_args;
 
 size_t sml_step_workspace_bytes(int64_t batch);

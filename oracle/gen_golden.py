@@ -206,7 +206,7 @@ def gen_eval(ns):
     npz("eval.npz", **out)
 
 
-def gen_period_run(ns, stop=False, news=False):
+def gen_period_run(ns, stop=False, news=False, opts=False):
     """End-to-end meta_train.run on a tiny stream, recording every batch the reference's
     DataLoaders produced so that the CUDA path can replay the same supplied triples."""
     U, I, NP, N, NNEG = 120, 150, 8, 96, 40
@@ -219,6 +219,8 @@ def gen_period_run(ns, stop=False, news=False):
     args.MF_batch_size = 32; args.TR_batch_size = 16; args.multi_num = 2
     args.MF_epochs = 1; args.TR_epochs = 1; args.pre_model = os.path.join(tmp, "pre.pkl")
     args.TR_stop_ = bool(stop)
+    if opts:        # the options that are off by default: --need_adaptive, --clip_grad (tight max norm so it bites), --norm
+        args.need_adaptive = True; args.clip_grad = True; args.maxnorm_grad = 0.05; args.norm = True
     if news:        # configs[2]: main_news.py settings (MF_epochs=2, TR_epochs=2) on a high-churn stream; data_name != 'yelp'
         args.data_name = "news"; args.MF_epochs = 2; args.TR_epochs = 2        # takes the other constructor branch (:314-325)
     torch.manual_seed(args.seed); np.random.seed(args.seed + 2)
@@ -292,7 +294,7 @@ def gen_period_run(ns, stop=False, news=False):
     out["args"] = np.array([args.MF_batch_size, args.TR_batch_size, args.multi_num, (2 if news else 1), args.TR_epochs,
                             args.seed], dtype=np.int64)
     out["hyper"] = np.array([args.MF_lr, args.l2, args.TR_lr, args.TR_l2], dtype=np.float64)
-    npz("period_run_news.npz" if news else ("period_run_stop.npz" if stop else "period_run.npz"), **out)
+    npz("period_run_opts.npz" if opts else ("period_run_news.npz" if news else ("period_run_stop.npz" if stop else "period_run.npz")), **out)
     # restore
     ns.transfer.PreSampleDatast = ns.dataset2.trainDataset_withPreSample
     ns.transfer.SampleDaset = ns.dataset.offlineDataset_withsample
@@ -323,7 +325,8 @@ def main():
     ns = ref_harness.load()
     gens = dict(transfer_fwd=gen_transfer_fwd, run_mf=gen_run_mf, mf_steps=gen_mf_steps, tr_steps=gen_tr_steps,
                 eval=gen_eval, period_run=gen_period_run, period_run_stop=lambda n: gen_period_run(n, stop=True),
-                period_run_news=lambda n: gen_period_run(n, news=True), select_neg=gen_select_neg)
+                period_run_news=lambda n: gen_period_run(n, news=True), period_run_opts=lambda n: gen_period_run(n, opts=True),
+                select_neg=gen_select_neg)
     for name, fn in gens.items():
         if a.only and name not in a.only.split(","):
             continue

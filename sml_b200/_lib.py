@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsml_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 D = 64
 OFF_C1W, OFF_C1B, OFF_C2W, OFF_C2B = 0, 32, 64, 128
 OFF_F1W, OFF_F1B, OFF_F2W, OFF_F2B = 160, 164000, 164512, 197280
@@ -35,6 +35,7 @@ class StepArgs(C.Structure):
         ("g_theta", _vp), ("m_theta", _vp), ("v_theta", _vp),
         ("loss_out", _vp), ("workspace", _vp), ("workspace_bytes", _sz), ("table_pitch", _i64),
         ("stamp_user", _vp), ("stamp_item", _vp),
+        ("adaptive_beta", _dbl), ("clip_max_norm", _dbl),
     ]
 
 
@@ -53,6 +54,8 @@ _PROTOS = {
     "sml_transfer_fwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),
     "sml_adam_tick": (_i32, [_vp, _dbl, _dbl, _dbl, _vp]),
     "sml_adam_dense": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _vp]),
+    "sml_sumsq": (_i32, [_vp, _i64, _vp, _vp, _vp]),
+    "sml_adam_dense_clipped": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _dbl, _dbl, _dbl, _dbl, _i32, _vp, _dbl, _vp]),
     "sml_adam_rows": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i32, _dbl, _dbl, _dbl, _vp]),
     "sml_adam_flush": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _dbl, _dbl, _dbl, _vp]),
     "sml_step_workspace_bytes": (_sz, [_i64]),

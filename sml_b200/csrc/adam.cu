@@ -22,19 +22,56 @@ __global__ void k_adam_tick(int64_t *state, double lr, double beta1, double beta
     if (threadIdx.x == 0 && blockIdx.x == 0) sml_adam_tick_body(state, lr, beta1, beta2);
 }
 
+// sum of squares with a fixed summation order (per-CTA partials, the last CTA adds them up): ||g||^2 for clip_grad_norm_
+__global__ void __launch_bounds__(256)
+k_sumsq(const float4 *__restrict__ g, int64_t n4, float *__restrict__ out, float *__restrict__ partials, unsigned int *__restrict__ ticket) {
+    sml_pdl_wait();
+    sml_pdl_trigger();
+    __shared__ float s_w[8];
+    __shared__ bool s_last;
+    float acc = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 x = g[i];
+        acc = fmaf(x.x, x.x, acc); acc = fmaf(x.y, x.y, acc); acc = fmaf(x.z, x.z, acc); acc = fmaf(x.w, x.w, acc);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += s_w[i];
+        partials[blockIdx.x] = t;
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        float t = 0.f;
+        for (unsigned i = 0; i < gridDim.x; ++i) t += __ldcg(partials + i);
+        *out = t;
+        *ticket = 0;
+    }
+}
+
 template <bool ZERO>
 __global__ void __launch_bounds__(256)
 k_adam_dense(float4 *__restrict__ p, float4 *__restrict__ m, float4 *__restrict__ v, float4 *__restrict__ g, int64_t n4,
-             const int64_t *__restrict__ state, float b1c, float beta2, float b2c, float eps, float wd) {
+             const int64_t *__restrict__ state, float b1c, float beta2, float b2c, float eps, float wd,
+             const float *__restrict__ sumsq, float max_norm) {
     sml_pdl_wait();
     sml_pdl_trigger();
+    // clip_grad_norm_: every gradient element times min(1, max_norm / (||g|| + 1e-6))
+    float gs = 1.0f;
+    if (sumsq) { const float c = max_norm / (sqrtf(__ldcg(sumsq)) + 1e-6f); gs = c < 1.0f ? c : 1.0f; }
     // b1c = (float)(1 - beta1), b2c = (float)(1 - beta2) are rounded from the double differences on the
     // host, as torch does (1.0f - 0.999f would be off by 5e-5 relative)
     const float *f = reinterpret_cast<const float *>(state + 1);
     const float step_size = f[0], bc2_sqrt = f[1];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 pp = p[i], mm = m[i], vv = v[i];
-        const float4 gg = g[i];
+        float4 gg = g[i];
+        if (sumsq) { gg.x *= gs; gg.y *= gs; gg.z *= gs; gg.w *= gs; }
         sml_adam1(pp.x, mm.x, vv.x, gg.x, b1c, beta2, b2c, step_size, bc2_sqrt, eps, wd);
         sml_adam1(pp.y, mm.y, vv.y, gg.y, b1c, beta2, b2c, step_size, bc2_sqrt, eps, wd);
         sml_adam1(pp.z, mm.z, vv.z, gg.z, b1c, beta2, b2c, step_size, bc2_sqrt, eps, wd);
@@ -153,6 +190,17 @@ int sml_launch_adam_rows(const SmlAdamRows *rows, int n_groups, const int64_t *s
     return SML_OK;
 }
 
+// partials: 1024 floats of scratch; ticket: one zeroed unsigned int (re-armed by the kernel)
+int sml_launch_sumsq(const float *g, int64_t n, float *sumsq, float *partials, unsigned int *ticket, cudaStream_t st) {
+    const int64_t n4 = n / 4;
+    int64_t blocks = (n4 + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    if (blocks < 1) blocks = 1;
+    SML_CUDA_OK(sml_launch(k_sumsq, dim3((unsigned)blocks), dim3(256), 0, st, (const float4 *)g, n4, sumsq, partials, ticket));
+    SML_LAUNCH_OK();
+    return SML_OK;
+}
+
 extern "C" {
 
 int sml_adam_tick(int64_t *state, double lr, double beta1, double beta2, void *stream) {
@@ -164,8 +212,21 @@ int sml_adam_tick(int64_t *state, double lr, double beta1, double beta2, void *s
     return SML_OK;
 }
 
+int sml_sumsq(const float *g, int64_t n, float *sumsq, void *scratch, void *stream) {
+    int rc = sml_check_device();
+    if (rc) return rc;
+    SML_REQUIRE(g && sumsq && scratch && n >= 0 && (n % 4) == 0, SML_E_BADARG, "sml_sumsq: bad arguments");
+    float *partials = (float *)scratch;
+    return sml_launch_sumsq(g, n, sumsq, partials, (unsigned int *)(partials + 1024), (cudaStream_t)stream);
+}
+
 int sml_adam_dense(float *p, float *m, float *v, float *g, int64_t n, const int64_t *state, double beta1, double beta2,
                    double eps, double weight_decay, int zero_grad, void *stream) {
+    return sml_adam_dense_clipped(p, m, v, g, n, state, beta1, beta2, eps, weight_decay, zero_grad, nullptr, 0.0, stream);
+}
+
+int sml_adam_dense_clipped(float *p, float *m, float *v, float *g, int64_t n, const int64_t *state, double beta1, double beta2,
+                           double eps, double weight_decay, int zero_grad, const float *sumsq, double max_norm, void *stream) {
     int rc = sml_check_device();
     if (rc) return rc;
     SML_REQUIRE(p && m && v && g && state, SML_E_BADARG, "sml_adam_dense: null pointer");
@@ -179,10 +240,10 @@ int sml_adam_dense(float *p, float *m, float *v, float *g, int64_t n, const int6
     if (blocks > cap) blocks = cap;
     if (zero_grad)
         SML_CUDA_OK(sml_launch(k_adam_dense<true>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (float4 *)p, (float4 *)m, (float4 *)v, (float4 *)g, n4,
-                               state, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps, (float)weight_decay));
+                               state, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps, (float)weight_decay, sumsq, (float)max_norm));
     else
         SML_CUDA_OK(sml_launch(k_adam_dense<false>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (float4 *)p, (float4 *)m, (float4 *)v, (float4 *)g, n4,
-                               state, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps, (float)weight_decay));
+                               state, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps, (float)weight_decay, sumsq, (float)max_norm));
     SML_LAUNCH_OK();
     return SML_OK;
 }

@@ -124,7 +124,7 @@ struct ConvBwdParams {
 // MODE 0: scatter into dense gradient table; MODE 1: write d_rows; THETA: accumulate conv grads
 template <int R, int MODE, bool THETA>
 __global__ void __launch_bounds__(CONV_THREADS)
-k_conv_bwd(ConvBwdParams P, const float *__restrict__ dA, float l2, float *__restrict__ d_rows) {
+k_conv_bwd(ConvBwdParams P, const float *__restrict__ dA, float l2, float *__restrict__ d_rows, float adaptive) {
     __shared__ ConvW sw;
     sml_pdl_wait();
     sml_pdl_trigger();
@@ -195,7 +195,14 @@ k_conv_bwd(ConvBwdParams P, const float *__restrict__ dA, float l2, float *__res
             }
             if (MODE == 0) {
                 // dense-gradient scatter: grad of l2*0.5*sum(w^2) is l2*w per occurrence (transfer.py:486)
-                atomicAdd(bg.g_tab + id * SML_D + lane + 32 * h, fmaf(l2, x1h, dx1));
+                float gsc = fmaf(l2, x1h, dx1);
+                if (adaptive != 0.f && gi == 0) {
+                    // --need_adaptive (transfer.py:490-499): beta * count_u / ||w_u||.detach() * ||w_u||^2 per distinct user
+                    // = 2 * beta * w_u / ||w_u|| per occurrence
+                    const float nh = sqrtf(warp_sum(x1[0] * x1[0] + x1[1] * x1[1]));
+                    gsc = fmaf(2.0f * adaptive / nh, x1h, gsc);
+                }
+                atomicAdd(bg.g_tab + id * SML_D + lane + 32 * h, gsc);
             } else if (d_rows) {
                 d_rows[(g.row0 + r) * SML_D + lane + 32 * h] = dx1;
             }
@@ -242,8 +249,8 @@ __global__ void __launch_bounds__(LOSS_THREADS)
 k_loss(const float *__restrict__ Y, const float *__restrict__ rowsq, int64_t B, int64_t rowP, int64_t rowN, int loss_kind,
        int normalize_user, float l2, float *__restrict__ dY, uint8_t *__restrict__ dYpk, float *__restrict__ scores,
        float *__restrict__ loss_out, float *__restrict__ partials, unsigned int *__restrict__ ticket,
-       float *__restrict__ gb_user, float *__restrict__ gb_item, float *__restrict__ zero_dA) {
-    __shared__ float s_part[LOSS_WARPS][3];
+       float *__restrict__ gb_user, float *__restrict__ gb_item, float *__restrict__ zero_dA, float adaptive) {
+    __shared__ float s_part[LOSS_WARPS][4];
     __shared__ float s_gb[2][SML_D];
     sml_pdl_wait();
     sml_pdl_trigger();
@@ -251,7 +258,7 @@ k_loss(const float *__restrict__ Y, const float *__restrict__ rowsq, int64_t B, 
     if (gb_user && threadIdx.x < 2 * SML_D) s_gb[threadIdx.x / SML_D][threadIdx.x % SML_D] = 0.f;
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    float acc_pos = 0.f, acc_neg = 0.f, acc_sq = 0.f;   // lane 0 only
+    float acc_pos = 0.f, acc_neg = 0.f, acc_sq = 0.f, acc_ad = 0.f;   // lane 0 only
     const float invB = 1.0f / (float)B;
     for (int64_t b = (int64_t)blockIdx.x * LOSS_WARPS + w; b < B; b += (int64_t)gridDim.x * LOSS_WARPS) {
         const float *yu = Y + b * SML_D, *yi = Y + (rowP + b) * SML_D, *yj = Y + (rowN + b) * SML_D;
@@ -288,7 +295,10 @@ k_loss(const float *__restrict__ Y, const float *__restrict__ rowsq, int64_t B, 
             dsp = -sml_sigmoid(-x);
             dsn = -dsp;
         }
-        if (rowsq && lane == 0) acc_sq += rowsq[b] + rowsq[rowP + b] + rowsq[rowN + b];
+        if (rowsq && lane == 0) {
+            acc_sq += rowsq[b] + rowsq[rowP + b] + rowsq[rowN + b];
+            if (adaptive != 0.f) acc_ad += sqrtf(rowsq[b]);           // sum over occurrences of ||w_u|| (transfer.py:490-499)
+        }
         if (scores && lane == 0) { scores[b] = sp; scores[B + b] = sn; }
         if (dY) {
 #pragma unroll
@@ -307,7 +317,7 @@ k_loss(const float *__restrict__ Y, const float *__restrict__ rowsq, int64_t B, 
             }
         }
     }
-    if (lane == 0) { s_part[w][0] = acc_pos; s_part[w][1] = acc_neg; s_part[w][2] = acc_sq; }
+    if (lane == 0) { s_part[w][0] = acc_pos; s_part[w][1] = acc_neg; s_part[w][2] = acc_sq; s_part[w][3] = acc_ad; }
     __syncthreads();
     if (gb_user) {
 #pragma unroll
@@ -317,9 +327,9 @@ k_loss(const float *__restrict__ Y, const float *__restrict__ rowsq, int64_t B, 
         else if (threadIdx.x < 2 * SML_D) atomicAdd(gb_item + threadIdx.x - SML_D, s_gb[1][threadIdx.x - SML_D]);
     }
     if (threadIdx.x == 0) {
-        float p = 0.f, n = 0.f, q = 0.f;
-        for (int i = 0; i < LOSS_WARPS; ++i) { p += s_part[i][0]; n += s_part[i][1]; q += s_part[i][2]; }
-        partials[3 * blockIdx.x + 0] = p; partials[3 * blockIdx.x + 1] = n; partials[3 * blockIdx.x + 2] = q;
+        float p = 0.f, n = 0.f, q = 0.f, ad = 0.f;
+        for (int i = 0; i < LOSS_WARPS; ++i) { p += s_part[i][0]; n += s_part[i][1]; q += s_part[i][2]; ad += s_part[i][3]; }
+        partials[4 * blockIdx.x + 0] = p; partials[4 * blockIdx.x + 1] = n; partials[4 * blockIdx.x + 2] = q; partials[4 * blockIdx.x + 3] = ad;
         __threadfence();
         const unsigned t = atomicAdd(ticket, 1u);
         s_last = (t == gridDim.x - 1);
@@ -327,14 +337,15 @@ k_loss(const float *__restrict__ Y, const float *__restrict__ rowsq, int64_t B, 
     __syncthreads();
     if (s_last && threadIdx.x == 0) {
         __threadfence();
-        float p = 0.f, n = 0.f, q = 0.f;
+        float p = 0.f, n = 0.f, q = 0.f, ad = 0.f;
         for (unsigned i = 0; i < gridDim.x; ++i) {
-            p += __ldcg(partials + 3 * i); n += __ldcg(partials + 3 * i + 1); q += __ldcg(partials + 3 * i + 2);
+            p += __ldcg(partials + 4 * i); n += __ldcg(partials + 4 * i + 1); q += __ldcg(partials + 4 * i + 2); ad += __ldcg(partials + 4 * i + 3);
         }
         float loss;
         if (loss_kind == SML_LOSS_BCE) loss = (-(p * invB)) + (-(n * invB));   // -mean - mean
         else loss = p;                                                           // -sum(logsigmoid)
         loss = loss + l2 * (0.5f * q);                                           // transfer.py:486-488
+        if (adaptive != 0.f) loss = loss + adaptive * ad;                        // :490-499
         loss_out[0] = loss;
         loss_out[1] += loss;
         *ticket = 0;   // re-arm for the next launch (graph replay)
@@ -378,7 +389,7 @@ int sml_launch_conv_fwd(const SmlRowGroup *groups, int n_groups, int variant, fl
 }
 
 int sml_launch_conv_bwd(const SmlConvBwdGroup *groups, int n_groups, int variant, const float *dA, float l2,
-                        float *d_rows, cudaStream_t st) {
+                        float *d_rows, cudaStream_t st, float adaptive) {
     SML_REQUIRE(n_groups >= 1 && n_groups <= MAX_GROUPS, SML_E_BADARG, "conv_bwd: bad group count %d", n_groups);
     ConvBwdParams P;
     P.n_groups = n_groups;
@@ -397,7 +408,7 @@ int sml_launch_conv_bwd(const SmlConvBwdGroup *groups, int n_groups, int variant
     // (96 per group measured 2-6 us slower per transfer step than 32, profiles/r01_tr_step_breakdown.md)
     if (theta) { const int cap = 32; if (gx > cap) gx = cap; }
     dim3 grid(gx, n_groups);
-#define SML_CB(R_, MODE_, TH_) SML_CUDA_OK(sml_launch(k_conv_bwd<R_, MODE_, TH_>, grid, dim3(CONV_THREADS), 0, st, P, dA, l2, d_rows))
+#define SML_CB(R_, MODE_, TH_) SML_CUDA_OK(sml_launch(k_conv_bwd<R_, MODE_, TH_>, grid, dim3(CONV_THREADS), 0, st, P, dA, l2, d_rows, adaptive))
     const bool com = variant == SML_VARIANT_COM;
     if (scatter) {
         if (theta) { if (com) SML_CB(3, 0, true); else SML_CB(2, 0, true); }
@@ -413,11 +424,11 @@ int sml_launch_conv_bwd(const SmlConvBwdGroup *groups, int n_groups, int variant
 
 int sml_launch_loss(const float *Y, const float *rowsq, int64_t B, int64_t row_pos, int64_t row_neg, int loss_kind,
                     int normalize_user, float l2, float *dY, uint8_t *dYpk, float *scores, float *loss_out, float *partials,
-                    unsigned int *ticket, cudaStream_t st, float *gb_user, float *gb_item, float *zero_dA) {
+                    unsigned int *ticket, cudaStream_t st, float *gb_user, float *gb_item, float *zero_dA, float adaptive) {
     int64_t blocks = (B + LOSS_WARPS - 1) / LOSS_WARPS;
-    if (blocks > 1024) blocks = 1024;   // partials[] holds 3 * 1024 floats
+    if (blocks > 1024) blocks = 1024;   // partials[] holds 4 * 1024 floats
     SML_CUDA_OK(sml_launch(k_loss, dim3((unsigned)blocks), dim3(LOSS_THREADS), 0, st, Y, rowsq, B, row_pos, row_neg, loss_kind, normalize_user,
-                           l2, dY, dYpk, scores, loss_out, partials, ticket, gb_user, gb_item, zero_dA));
+                           l2, dY, dYpk, scores, loss_out, partials, ticket, gb_user, gb_item, zero_dA, adaptive));
     SML_LAUNCH_OK();
     return SML_OK;
 }

@@ -154,8 +154,9 @@ struct SmlConvBwdGroup {
     float *g_tab;      // dense gradient table for scatter (mode 0) or null
     float *g_theta;    // this group's net gradient block or null
 };
+// adaptive (scatter mode, first group = the user rows): adds 2 * adaptive * x_hat / ||x_hat|| per occurrence (--need_adaptive)
 int sml_launch_conv_bwd(const SmlConvBwdGroup *groups, int n_groups, int variant, const float *dA, float l2,
-                        float *d_rows, cudaStream_t st);
+                        float *d_rows, cudaStream_t st, float adaptive = 0.f);
 
 // Generic SIMT fp32 GEMM (grouped over blockIdx.z):  C[M,N] = epi(opA(A)[M,K] * opB(B)[K,N])
 enum { SML_A_MK = 0, SML_A_MK_GELU = 1, SML_A_KM = 2, SML_A_KM_GELU = 3 };   // A stored [m][k] / + gelu on load / [k][m] / + gelu
@@ -183,7 +184,8 @@ int sml_launch_colsum(const SmlColsumProb *probs, int n_probs, cudaStream_t st);
 int sml_launch_loss(const float *Y, const float *rowsq, int64_t B, int64_t row_pos, int64_t row_neg, int loss_kind,
                     int normalize_user, float l2, float *dY, uint8_t *dYpk, float *scores, float *loss_out, float *partials,
                     unsigned int *ticket, cudaStream_t st, float *gb_user = nullptr, float *gb_item = nullptr,
-                    float *zero_dA = nullptr);   // zero_dA (optional): dA[N,320] rows of the batch are cleared (split-K d1)
+                    float *zero_dA = nullptr,    // zero_dA (optional): dA[N,320] rows of the batch are cleared (split-K d1)
+                    float adaptive = 0.f);       // --need_adaptive: + adaptive * sum_b ||x_hat user row b|| (needs rowsq)
 
 // tcgen05 GEMM with pre-packed operands (umma_packed.cu)
 enum { SML_PK_FC1 = 0, SML_PK_FC2 = 1, SML_PK_D2 = 2, SML_PK_D1 = 3 };
@@ -215,6 +217,7 @@ constexpr size_t SML_PK_THETA_BYTES = 3538944;
 int sml_launch_pack_theta(const float *theta, uint8_t *out, int n_nets, cudaStream_t st, int64_t *adam_state = nullptr, double lr = 0.0);
 
 int sml_launch_row_normalize(float *Y, int64_t n, cudaStream_t st);
+int sml_launch_sumsq(const float *g, int64_t n, float *sumsq, float *partials, unsigned int *ticket, cudaStream_t st);
 
 // fused transfer forward (umma_fused_fwd.cu): one persistent kernel for conv -> fc1 -> GELU -> fc2 over a stream of rows.
 // wpk = the net's W1 / W2 packed by sml_launch_pack_fused (sml_fused_fwd_packed_bytes() bytes).

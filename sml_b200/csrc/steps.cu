@@ -30,7 +30,7 @@ Rows rows_of(int64_t B) {
 
 struct StepWs {
     unsigned int *ticket;   // [64] (only [0] used), re-armed by k_loss
-    float *partials;        // [3 * 1024]
+    float *partials;        // [4 * 1024]
     float *A, *Z1, *Y, *dY, *dZ1, *dA, *rowsq;          // plain, R rows
     uint8_t *Apk, *Gpk, *dYpk, *dZpk;                   // packed operands (128-row tiles over the R rows)
     uint8_t *theta_pk;                                  // packed weights, 2 nets
@@ -39,7 +39,7 @@ struct StepWs {
 size_t step_ws_bytes(int64_t B) {
     const Rows r = rows_of(B);
     const size_t R = (size_t)r.R, T = R / 128;
-    size_t n = 256 + 3 * 1024 * sizeof(float) + R * (320 + 512 + 64 + 64 + 512 + 320 + 1) * sizeof(float);
+    size_t n = 256 + 4 * 1024 * sizeof(float) + R * (320 + 512 + 64 + 64 + 512 + 320 + 1) * sizeof(float);
     n += T * (size_t)(10 + 16 + 2 + 16) * pk_block_bytes(128) + 2 * SML_PK_THETA_BYTES;
     return n + 16 * 256;
 }
@@ -51,7 +51,7 @@ StepWs carve(void *ws, int64_t B) {
     const Rows r = rows_of(B);
     const size_t R = (size_t)r.R, T = R / 128;
     w.ticket = (unsigned int *)take(256);
-    w.partials = (float *)take(3 * 1024 * sizeof(float));
+    w.partials = (float *)take(4 * 1024 * sizeof(float));
     w.A = (float *)take(R * 320 * sizeof(float));
     w.Z1 = (float *)take(R * 512 * sizeof(float));
     w.Y = (float *)take(R * 64 * sizeof(float));          // Y and dA are adjacent: one memset clears both when the
@@ -143,7 +143,8 @@ SideStream *side_stream() {
 // g_theta != null (tensor-core path): the fc2 / fc1 bias gradients are accumulated by the loss kernel and by the d2
 // epilogue.  tick_state != null: the Adam tick rides in the theta packer's launch.
 int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, bool need_plain_A, bool pack_theta, float l2,
-                     float *scores, cudaStream_t st, float *g_theta = nullptr, int64_t *tick_state = nullptr, double tick_lr = 0.0) {
+                     float *scores, cudaStream_t st, float *g_theta = nullptr, int64_t *tick_state = nullptr, double tick_lr = 0.0,
+                     float adaptive = 0.f) {
     const Rows r = rows_of(a->batch);
     const int64_t B = r.B;
     const float *tu = a->theta, *ti = a->theta + SML_NET_STRIDE;
@@ -200,7 +201,7 @@ int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, b
     const int dbg = sml_debug_mask();
     if (dbg & 8) return SML_OK;
     rc = sml_launch_loss(w.Y, want_rowsq ? w.rowsq : nullptr, B, r.Bp, r.Bp + B, a->loss, a->variant == SML_VARIANT_CONV, l2, w.dY,
-                         tc ? w.dYpk : nullptr, scores, a->loss_out, w.partials, w.ticket, st, gbu2, gbi2, zero_dA ? w.dA : nullptr);
+                         tc ? w.dYpk : nullptr, scores, a->loss_out, w.partials, w.ticket, st, gbu2, gbi2, zero_dA ? w.dA : nullptr, adaptive);
     if (rc) return rc;
     if (dbg & 4) return SML_OK;
     // dZ1 = (dY W2) * GELU'(Z1)
@@ -296,7 +297,7 @@ int mf_step_impl(const sml_step_args *a, bool pack_theta, void *stream) {
         rc = sml_launch_adam_rows(ar, 3, a->adam_state, 0, 0.9, 0.999, 1e-8, st);
         if (rc) return rc;
     }
-    rc = forward_and_loss(a, w, true, false, pack_theta, (float)a->l2, nullptr, st);
+    rc = forward_and_loss(a, w, true, false, pack_theta, (float)a->l2, nullptr, st, nullptr, nullptr, 0.0, (float)a->adaptive_beta);
     if (rc) return rc;
     const int dbg = sml_debug_mask();                  // profiling aid (sml_debug_set_mask): 0 in production
     if (dbg & (4 | 8 | 128 | 256)) return SML_OK;
@@ -306,7 +307,7 @@ int mf_step_impl(const sml_step_args *a, bool pack_theta, void *stream) {
         SmlRowGroup g[3];
         make_groups(a, g);
         SmlConvBwdGroup bg[3] = {{g[0], a->g_user, nullptr}, {g[1], a->g_item, nullptr}, {g[2], a->g_item, nullptr}};
-        rc = sml_launch_conv_bwd(bg, 3, a->variant, w.dA, (float)a->l2, nullptr, st);
+        rc = sml_launch_conv_bwd(bg, 3, a->variant, w.dA, (float)a->l2, nullptr, st, (float)a->adaptive_beta);
         if (rc) return rc;
     }
     if (dbg & 64) return SML_OK;
@@ -457,6 +458,14 @@ int sml_tr_step(const sml_step_args *a, void *stream) {
     if (!(dbg & 1)) SML_CUDA_OK(cudaStreamWaitEvent(st, ss->join, 0));
     if (dbg & 64) return SML_OK;
     // Adam with coupled L2 (weight_decay = TR_l2, model/transfer.py:393) over the whole theta block
+    if (a->clip_max_norm > 0.0) {
+        // --clip_grad (model/transfer.py:723-727): g *= min(1, max_norm / (||g||_2 + 1e-6)) over ALL transfer parameters
+        float *sumsq = reinterpret_cast<float *>(w.ticket + 2);
+        rc = sml_launch_sumsq(a->g_theta, 2 * (int64_t)SML_NET_STRIDE, sumsq, w.partials, w.ticket + 1, st);
+        if (rc) return rc;
+        return sml_adam_dense_clipped(a->theta, a->m_theta, a->v_theta, a->g_theta, 2 * (int64_t)SML_NET_STRIDE, a->adam_state, 0.9, 0.999,
+                                      1e-8, a->l2, 1, sumsq, a->clip_max_norm, stream);
+    }
     return sml_adam_dense(a->theta, a->m_theta, a->v_theta, a->g_theta, 2 * (int64_t)SML_NET_STRIDE, a->adam_state, 0.9, 0.999,
                           1e-8, a->l2, 1, stream);
 }

@@ -109,10 +109,14 @@ class meta_train(object):
         if laten_dim != 64:
             raise ValueError("sml_b200 kernels are specialised for laten=64 (the reference default)")
         if getattr(args, "TR_with_MF_bias", False):
-            raise NotImplementedError("TR_with_MF_bias (65-wide transfer input) is not supported; reference default is False")
-        if getattr(args, "clip_grad", False) or getattr(args, "need_adaptive", False) or getattr(args, "norm", False):
-            raise NotImplementedError("clip_grad / need_adaptive / norm are off in the reference's final version "
-                                      "(main_yelp.py:50-55,104) and are not implemented")
+            # the reference concatenates the bias column into 65-wide rows (model/transfer.py:347-355,918-921) and only its unused
+            # transfer2 / GRU / transfer3 modules take that width; ConvTransfer(_com)(64, 64) fails on the shape there too
+            raise NotImplementedError("TR_with_MF_bias (65-wide transfer input) is not supported by conv / conv_com (nor by the "
+                                      "reference with these transfer types); reference default is False")
+        if getattr(args, "norm", False) and args.transfer_type == "conv":
+            # ConvTransfer.run_MF divides the score by the (attached) norm of the already normalised user row
+            # (model/conv_transfer.py:80-83); conv_com's BCE branch ignores ``norm`` altogether (:122-126), which is what runs below
+            raise NotImplementedError("norm=True with transfer_type='conv' is not implemented (off in the reference's final version)")
         self.batch_source = batch_source
         self.emulate_reference_rng = emulate_reference_rng
         self.device_sampler = device_sampler
@@ -369,17 +373,20 @@ class meta_train(object):
         self._loss.zero_()
         nb = -(-n // B)
         lr = self.MF_optimizer.param_groups[0]["lr"]
+        # --need_adaptive (model/transfer.py:490-499, beta = 0.1).  --clip_grad in this loop clips the gradients of theta,
+        # which no optimizer applies here (:507-511): nothing to do.  --norm reaches run_MF's BPR branch only (BCE ignores it).
+        adaptive = 0.1 if getattr(args, "need_adaptive", False) else 0.0
         def build(u, i, j):
             return ops.make_step_args(user=u, item=i, neg=j, batch=B,
                                       last_user=self.last_user_weight, last_item=self.last_item_weight,
                                       hat_user=uw, hat_item=iw, theta=self.transfer.theta, variant=self.transfer.variant,
                                       loss=ops.LOSS_BCE if self.transfer.variant == ops.VARIANT_COM else ops.LOSS_BPR,
                                       adam_state=self.MF_optimizer.adam_state, lr=lr, l2=args.l2, loss_out=self._loss,
-                                      workspace=ws, **self._mf, **self._stamps)
+                                      adaptive_beta=adaptive, workspace=ws, **self._mf, **self._stamps)
         self._tab_version += 1
         # every pointer / scalar baked into the captured StepArgs is part of the graph key
         self._run_epoch("mf", build, (user, item, neg), n, B,
-                        (lr, args.l2, self.transfer.variant) + tuple(t.data_ptr() for t in (
+                        (lr, args.l2, self.transfer.variant, adaptive) + tuple(t.data_ptr() for t in (
                             uw, iw, self.last_user_weight, self.last_item_weight, self.transfer.theta, ws,
                             self.MF_optimizer.adam_state, *self._mf.values(), *self._stamps.values())))
         return self._loss[1].item() / nb
@@ -474,6 +481,7 @@ class meta_train(object):
         self._loss.zero_()
         nb = -(-n // B)
         g = self.transfer_optimizer.param_groups[0]
+        clip = float(args.maxnorm_grad) if getattr(args, "clip_grad", False) else 0.0       # model/transfer.py:723-727
         def build(u, i, j):
             return ops.make_step_args(user=u, item=i, neg=j, batch=B,
                                       last_user=self.last_user_weight, last_item=self.last_item_weight,
@@ -482,9 +490,9 @@ class meta_train(object):
                                       loss=ops.LOSS_BCE if self.transfer.variant == ops.VARIANT_COM else ops.LOSS_BPR,
                                       adam_state=self.transfer_optimizer.adam_state, lr=g["lr"], l2=g["weight_decay"],
                                       g_theta=self.transfer.theta_grad, m_theta=self._tr["m"], v_theta=self._tr["v"],
-                                      loss_out=self._loss, workspace=ws)
+                                      loss_out=self._loss, workspace=ws, clip_max_norm=clip)
         self._run_epoch("tr", build, (user, item, neg), n, B,
-                        (g["lr"], g["weight_decay"], self.transfer.variant) + tuple(t.data_ptr() for t in (
+                        (g["lr"], g["weight_decay"], self.transfer.variant, clip) + tuple(t.data_ptr() for t in (
                             self.transfer.theta, self.transfer.theta_grad, self._tr["m"], self._tr["v"], ws,
                             self.last_user_weight, self.last_item_weight, self.user_weight_hat, self.item_weight_hat,
                             self.transfer_optimizer.adam_state)))

@@ -12,11 +12,11 @@ from tests.test_host_logic import make_args, write_fixture_stream
 pytestmark = pytest.mark.gpu
 
 
-def run_ours(g, tmp, stop, replay, news=False):
+def run_ours(g, tmp, stop, replay, news=False, opts=False):
     from sml_b200.data.dataset2 import transfer_data
     from sml_b200.model.transfer import meta_train
     NP, U, I = write_fixture_stream(g, tmp)
-    args = make_args(g, tmp, stop, news=news)
+    args = make_args(g, tmp, stop, news=news, opts=opts)
     torch.manual_seed(args.seed); np.random.seed(args.seed + 2)
     ds = transfer_data(args, path=args.data_path, datasetname="mini", file_path_list=[str(i) for i in range(NP)],
                        test_list=[str(j) for j in range(5, NP)], validation_list=None, online_train_time=2, online_test_time=5)
@@ -55,7 +55,7 @@ def run_ours(g, tmp, stop, replay, news=False):
 @pytest.mark.parametrize("replay", [True, False])
 def test_period_run_matches_reference(golden, tmp_path, name, stop, replay):
     g = golden(name)
-    meta = run_ours(g, str(tmp_path), stop, replay, news=name.endswith("news"))
+    meta = run_ours(g, str(tmp_path), stop, replay, news=name.endswith("news"), opts=name.endswith("opts"))
     fu = meta.MFbase.user_laten.weight.data.cpu().numpy()
     fi = meta.MFbase.item_laten.weight.data.cpu().numpy()
     # Differences against the reference grow ~10x per period on these tiny streams (chaotic training dynamics: the fp32
@@ -68,7 +68,7 @@ def test_period_run_matches_reference(golden, tmp_path, name, stop, replay):
     # end-of-stream item table, element-wise relative to its scale: measured 0.5e-4 .. 2.5e-4 (Yelp-like, 3 periods of drift),
     # 1.1e-5 .. 1.4e-5 (transfer frozen) and 1.1e-2 .. 1.3e-2 (news-like: 2 + 2 epochs on a churning item set amplify ~10x per
     # period) over repeated runs; the bounds sit ~4x above
-    item_tol = {"period_run": 1e-3, "period_run_stop": 1e-4, "period_run_news": 5e-2}[name]
+    item_tol = {"period_run": 1e-3, "period_run_stop": 1e-4, "period_run_news": 5e-2, "period_run_opts": 1e-3}[name]
     assert np.abs(fi - g["final_item"]).max() < item_tol * np.abs(g["final_item"]).max()
     assert np.abs(meta.user_weight_hat.cpu().numpy() - g["final_user_hat"]).max() < loose * max(1.0, np.abs(g["final_user_hat"]).max())
     for net in ("user", "item"):
@@ -109,17 +109,21 @@ def test_period_run_matches_reference(golden, tmp_path, name, stop, replay):
     assert meta.MF_optimizer.step_count == n_mf
 
 
-@pytest.mark.parametrize("name", ["period_run", "period_run_news"])
+@pytest.mark.parametrize("name", ["period_run", "period_run_news", "period_run_opts"])
 def test_first_period_within_tolerance(golden, tmp_path, name):
     """north_star: fp32 embeddings and theta within 1e-4 (relative) after one period's updates.  The fixture stores
-    sum / abs-sum checksums of both tables and of theta after every period of the reference's run."""
+    sum / abs-sum checksums of both tables and of theta after every period of the reference's run.
+    ``period_run_opts`` is the reference's run with --need_adaptive --clip_grad (maxnorm 0.05) --norm: the options that are
+    off by default (model/transfer.py:490-499,507-510,723-727).  With them the mini stream collapses every user row onto
+    the same vector within three periods and the end state is hypersensitive (two runs of this package differ by 0.3 there),
+    so the options are pinned on the first period only."""
     import contextlib, io
     from sml_b200.data.dataset2 import transfer_data
     from sml_b200.model.transfer import meta_train
     g = golden(name)
     tmp = str(tmp_path)
     NP, U, I = write_fixture_stream(g, tmp)
-    args = make_args(g, tmp, False, news=name.endswith("news"))
+    args = make_args(g, tmp, False, news=name.endswith("news"), opts=name.endswith("opts"))
     torch.manual_seed(args.seed); np.random.seed(args.seed + 2)
     ds = transfer_data(args, path=args.data_path, datasetname="mini", file_path_list=[str(i) for i in range(NP)],
                        test_list=[str(j) for j in range(5, NP)], validation_list=None, online_train_time=2, online_test_time=5)

@@ -17,9 +17,16 @@ from sml_b200.data.dataset2 import transfer_data, trainDataset_withPreSample
 from sml_b200.model.transfer import meta_train
 
 
-def make_args(g, tmp, stop=False, news=False):
+def make_args(g, tmp, stop=False, news=False, opts=False):
     mfb, trb, multi, mfe, tre, seed = (int(x) for x in g["args"])
     lr, l2, trlr, trl2 = (float(x) for x in g["hyper"])
+    a = _make_args(g, tmp, stop, news, mfb, trb, multi, mfe, tre, seed, lr, l2, trlr, trl2)
+    if opts:        # oracle/gen_golden.py: gen_period_run(opts=True)
+        a.need_adaptive = True; a.clip_grad = True; a.maxnorm_grad = 0.05; a.norm = True
+    return a
+
+
+def _make_args(g, tmp, stop, news, mfb, trb, multi, mfe, tre, seed, lr, l2, trlr, trl2):
     return argparse.Namespace(
         data_name="news" if news else "yelp", data_path=tmp + "/", multi_num=multi, MF_lr=lr, MF_epochs=mfe, l2=l2, MF_batch_size=mfb, laten=64,
         pre_model=os.path.join(tmp, "pre.pt"), MF_sample="all", Load_W_hat=False, clip_grad=False, need_adaptive=False,
