@@ -246,6 +246,20 @@ int sml_pack_rows(const float *tab, const int64_t *ids, int64_t n_rows, int d, v
 int sml_fullcat_rank(const void *users_packed, const void *items_packed, const float *s_pos, const int64_t *pos_id, int64_t n_users,
                      int64_t n_items, int64_t item_id0, int32_t *gt, int32_t *eq, void *stream);
 
+/* The positive's score from the SAME tensor-core arithmetic as the catalog scores (so that the counts of sml_fullcat_rank are
+ * self-consistent: a catalog item equal to the positive ties exactly): s_pos[u] = score of user row u of users_packed with row
+ * u of pos_packed (= sml_pack_rows of the item table gathered by the positives' ids). */
+int sml_fullcat_pos_scores(const void *users_packed, const void *pos_packed, int64_t n_users, float *s_pos, void *stream);
+/* Full-catalog top-k (north_star item 3): for every user row of users_packed the k (<= 64) highest-scoring items of
+ * items_packed (n_items items, global ids from item_id0), scores descending -- out_scores / out_ids [n_users, k]; the item
+ * exclude_id[u] is skipped when exclude_id is non-null; NaN scores rank highest (torch.topk); entries beyond the catalog size
+ * are (-inf, -1).  Fused into the score GEMM's epilogue: each epilogue thread keeps the k best of the columns it sees (a
+ * register threshold, the list in scratch; ~k ln(n_items / k) insertions per row), one merge launch combines the lists.
+ * Catalog shards on several GPUs: run per shard, concatenate, select again. */
+size_t sml_fullcat_topk_workspace_bytes(int64_t n_users, int64_t n_items, int k);
+int sml_fullcat_topk(const void *users_packed, const void *items_packed, const int64_t *exclude_id, int64_t n_users, int64_t n_items,
+                     int64_t item_id0, int k, float *out_scores, int64_t *out_ids, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- row exchange for row-sharded tables (north_star item 4) ---------------------------------
  * Tables are sharded by id (owner = id % world, local row = id / world).  Owner side of the exchange:
  *   sml_gather_pairs : out[n] = [last[loc[n]] | hat[loc[n]]]   (2*d floats per id; answers an id request)

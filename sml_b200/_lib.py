@@ -68,6 +68,9 @@ _PROTOS = {
     "sml_packed_rows_bytes": (_sz, [_i64]),
     "sml_pack_rows": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "sml_fullcat_rank": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "sml_fullcat_pos_scores": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "sml_fullcat_topk_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "sml_fullcat_topk": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "sml_philox_negatives": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, C.c_uint64, C.c_uint64, _vp, _vp]),
     "sml_gather_pairs": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "sml_scatter_grads": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _dbl, _dbl, _vp]),

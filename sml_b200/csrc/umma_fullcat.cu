@@ -28,10 +28,21 @@ constexpr int FC_STAGES = 2;
 constexpr uint32_t FC_TILE_BYTES = 2 * pk_block_bytes(128);   // 2 K chunks (K = 64), hi + lo: 73 728 B
 constexpr uint32_t FC_SMEM = (1 + FC_STAGES) * FC_TILE_BYTES + 128;
 
+// MODE 0: rank counts of the positive (gt / eq).  MODE 1: the diagonal of the score tile -- score of user u with the u-th row of
+// the "item" operand (its gathered positive item), i.e. the positive's score from the very same tensor-core arithmetic the
+// catalog scores come from.  MODE 2: per-thread top-K candidate lists (merged by k_fullcat_topk_merge).
+struct FcTopk {
+    float *scores;      // [gridDim.y * gridDim.x * 256][K]  (CTA-major, thread, slot)
+    int64_t *ids;
+    int *counts;        // [gridDim.y * gridDim.x * 256]
+    int K;
+};
+
+template <int MODE>
 __global__ void __launch_bounds__(FC_THREADS, 1)
 k_fullcat_rank(const uint8_t *__restrict__ Upk, const uint8_t *__restrict__ Ipk, const float *__restrict__ s_pos,
                const int64_t *__restrict__ pos_id, int64_t n_users, int64_t n_items, int64_t item_id0, int tiles_per_split,
-               int *__restrict__ gt, int *__restrict__ eq) {
+               int *__restrict__ gt, int *__restrict__ eq, float *__restrict__ diag_out, FcTopk T) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *sA = smem;
     uint8_t *sB = smem + FC_TILE_BYTES;
@@ -40,11 +51,14 @@ k_fullcat_rank(const uint8_t *__restrict__ Upk, const uint8_t *__restrict__ Ipk,
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_item_tiles = (n_items + 127) / 128;
-    const int64_t t0 = (int64_t)blockIdx.x * tiles_per_split;
-    const int64_t t1 = t0 + tiles_per_split < n_item_tiles ? t0 + tiles_per_split : n_item_tiles;
-    const int ntiles = (int)(t1 - t0);
-    if (ntiles <= 0) return;
     const int ut = blockIdx.y;
+    const int64_t t0 = MODE == 1 ? (int64_t)ut : (int64_t)blockIdx.x * tiles_per_split;      // diagonal: user tile t against "item" tile t
+    const int64_t t1 = MODE == 1 ? t0 + 1 : (t0 + tiles_per_split < n_item_tiles ? t0 + tiles_per_split : n_item_tiles);
+    const int ntiles = (int)(t1 - t0);
+    if (ntiles <= 0) {
+        if (MODE == 2 && threadIdx.x >= 64) T.counts[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 256 + (threadIdx.x - 64)] = 0;
+        return;
+    }
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
@@ -103,10 +117,17 @@ k_fullcat_rank(const uint8_t *__restrict__ Upk, const uint8_t *__restrict__ Ipk,
         const int quarter = warp & 3, chalf = (warp - 2) >> 2;
         const int64_t u = (int64_t)ut * 128 + quarter * 32 + lane;
         const bool live = u < n_users;
-        const float sp = live ? __ldg(s_pos + u) : 0.f;
-        const int64_t pid = live ? __ldg(pos_id + u) : -1;
+        const float sp = (MODE == 0 && live) ? __ldg(s_pos + u) : 0.f;
+        const int64_t pid = (MODE != 1 && live && pos_id) ? __ldg(pos_id + u) : -1;
         const bool sp_nan = sp != sp;
         int c_gt = 0, c_eq = 0;
+        // MODE 2: this thread's candidate list (unsorted, the minimum tracked): K slots in global scratch, touched only on the
+        // rare insertion (~K ln(N / K) times over N items)
+        const size_t tslot = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 256 + (threadIdx.x - 64);
+        float *lsc = MODE == 2 ? T.scores + tslot * T.K : nullptr;
+        int64_t *lid = MODE == 2 ? T.ids + tslot * T.K : nullptr;
+        float thr = -INFINITY;
+        int cnt = 0, amin = 0;
         for (int j = 0; j < ntiles; ++j) {
             const int acc = j & 1;
             mbar_wait(&acc_full[acc], (j >> 1) & 1);
@@ -116,27 +137,98 @@ k_fullcat_rank(const uint8_t *__restrict__ Upk, const uint8_t *__restrict__ Ipk,
             for (int c0 = chalf * 64; c0 < chalf * 64 + 64; c0 += 32) {
                 float v[32];
                 tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + acc * 128 + c0, v);
+                if (MODE == 1) {
+                    // the diagonal: user row r of the tile against item row r of the tile
+                    const int r = quarter * 32 + lane;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int64_t it = item0 + c0 + i;
-                    const bool ok = (it - item_id0) < n_items && it != pid;
-                    const bool vn = v[i] != v[i];
-                    c_gt += ok && ((v[i] > sp) || (vn && !sp_nan));
-                    c_eq += ok && ((v[i] == sp) || (vn && sp_nan));
+                    for (int i = 0; i < 32; ++i)
+                        if (c0 + i == r && live && j == 0) diag_out[u] = v[i];
+                } else if (MODE == 0) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int64_t it = item0 + c0 + i;
+                        const bool ok = (it - item_id0) < n_items && it != pid;
+                        const bool vn = v[i] != v[i];
+                        c_gt += ok && ((v[i] > sp) || (vn && !sp_nan));
+                        c_eq += ok && ((v[i] == sp) || (vn && sp_nan));
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int64_t it = item0 + c0 + i;
+                        const float sc = (v[i] != v[i]) ? INFINITY : v[i];               // NaN ranks highest, like torch.topk
+                        if (live && (it - item_id0) < n_items && it != pid && (cnt < T.K || sc > thr)) {
+                            if (cnt < T.K) {
+                                lsc[cnt] = sc; lid[cnt] = it; ++cnt;
+                            } else {
+                                lsc[amin] = sc; lid[amin] = it;
+                            }
+                            if (cnt == T.K) {                                            // new minimum of the full list
+                                float m = lsc[0]; int am = 0;
+                                for (int k = 1; k < T.K; ++k) { const float x = lsc[k]; if (x < m) { m = x; am = k; } }
+                                thr = m; amin = am;
+                            }
+                        }
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[acc]);
         }
-        if (live) {
+        if (MODE == 0 && live) {
             if (c_gt) atomicAdd(gt + u, c_gt);
             if (c_eq) atomicAdd(eq + u, c_eq);
         }
+        if (MODE == 2) T.counts[tslot] = cnt;
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<256>(tmem);
+}
+
+// Merge of the per-thread candidate lists of one user (2 column halves x `splits` item ranges) into its top K, descending:
+// one warp per user, K rounds of a warp-wide arg-max over at most 2 * splits * K candidates.
+__global__ void __launch_bounds__(256)
+k_fullcat_topk_merge(FcTopk T, int splits, int64_t n_users, float *__restrict__ out_scores, int64_t *__restrict__ out_ids) {
+    const int lane = threadIdx.x & 31;
+    const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (u >= n_users) return;
+    const int64_t ut = u >> 7;
+    const int r = (int)(u & 127), quarter = r >> 5, l = r & 31;
+    const int ncand = 2 * splits * T.K;
+    for (int k = 0; k < T.K; ++k) {
+        float best = -INFINITY;
+        int bc = -1;
+        for (int c = lane; c < ncand; c += 32) {
+            const int list = c / T.K, slot = c - list * T.K, split = list >> 1, chalf = list & 1;
+            const size_t tslot = ((size_t)ut * splits + split) * 256 + (size_t)(chalf * 4 + ((quarter + 2) & 3)) * 32 + l;   // epilogue warp 2 + e: quarter = warp & 3
+            if (slot < __ldg(T.counts + tslot)) {
+                const float x = T.scores[tslot * T.K + slot];
+                if (bc < 0 || x > best) { best = x; bc = c; }
+            }
+        }
+        // warp arg-max (ties: the lowest candidate index, deterministic)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+            if (oc >= 0 && (bc < 0 || ob > best || (ob == best && oc < bc))) { best = ob; bc = oc; }
+        }
+        if (bc < 0) {                                       // fewer than K items in the catalog
+            if (lane == 0) { out_scores[u * T.K + k] = -INFINITY; out_ids[u * T.K + k] = -1; }
+            continue;
+        }
+        const int list = bc / T.K, slot = bc - list * T.K, split = list >> 1, chalf = list & 1;
+        const size_t tslot = ((size_t)ut * splits + split) * 256 + (size_t)(chalf * 4 + ((quarter + 2) & 3)) * 32 + l;
+        if (lane == 0) {
+            out_scores[u * T.K + k] = best;
+            out_ids[u * T.K + k] = T.ids[tslot * T.K + slot];
+            T.scores[tslot * T.K + slot] = -INFINITY;       // taken; -inf entries never win again unless nothing else is left
+            T.ids[tslot * T.K + slot] = -1;
+        }
+        __syncwarp();
+    }
 }
 
 // rows of a table (optionally gathered by ids) -> packed K-major operand with K = 64 (2 chunks), 128-row tiles
@@ -181,17 +273,25 @@ int sml_pack_rows(const float *tab, const int64_t *ids, int64_t n_rows, int d, v
     return SML_OK;
 }
 
+static int fullcat_attr() {
+    static bool attr_set = false;
+    if (!attr_set) {
+        SML_CUDA_OK(cudaFuncSetAttribute(k_fullcat_rank<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FC_SMEM));
+        SML_CUDA_OK(cudaFuncSetAttribute(k_fullcat_rank<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FC_SMEM));
+        SML_CUDA_OK(cudaFuncSetAttribute(k_fullcat_rank<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FC_SMEM));
+        attr_set = true;
+    }
+    return SML_OK;
+}
+
 int sml_fullcat_rank(const void *users_packed, const void *items_packed, const float *s_pos, const int64_t *pos_id, int64_t n_users,
                      int64_t n_items, int64_t item_id0, int32_t *gt, int32_t *eq, void *stream) {
     int rc = sml_check_device();
     if (rc) return rc;
     if (n_users <= 0 || n_items <= 0) return SML_OK;
     SML_REQUIRE(users_packed && items_packed && s_pos && pos_id && gt && eq, SML_E_BADARG, "sml_fullcat_rank: null pointer");
-    static bool attr_set = false;
-    if (!attr_set) {
-        SML_CUDA_OK(cudaFuncSetAttribute(k_fullcat_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FC_SMEM));
-        attr_set = true;
-    }
+    rc = fullcat_attr();
+    if (rc) return rc;
     const int64_t ut = (n_users + 127) / 128, it = (n_items + 127) / 128;
     // split the item tiles so that user_tiles x splits covers the SMs a few times over, but keep >= 8 tiles per CTA
     // to amortise the A-tile load and the pipeline fill
@@ -204,8 +304,72 @@ int sml_fullcat_rank(const void *users_packed, const void *items_packed, const f
     splits = (it + per - 1) / per;
     SML_REQUIRE(ut <= 65535, SML_E_UNSUPPORTED, "sml_fullcat_rank: at most 65535*128 users per call (got %lld)", (long long)n_users);
     dim3 grid((unsigned)splits, (unsigned)ut);
-    k_fullcat_rank<<<grid, FC_THREADS, FC_SMEM, (cudaStream_t)stream>>>((const uint8_t *)users_packed, (const uint8_t *)items_packed, s_pos,
-                                                                        pos_id, n_users, n_items, item_id0, (int)per, gt, eq);
+    k_fullcat_rank<0><<<grid, FC_THREADS, FC_SMEM, (cudaStream_t)stream>>>((const uint8_t *)users_packed, (const uint8_t *)items_packed, s_pos,
+                                                                           pos_id, n_users, n_items, item_id0, (int)per, gt, eq, nullptr, FcTopk{});
+    SML_LAUNCH_OK();
+    return SML_OK;
+}
+
+int sml_fullcat_pos_scores(const void *users_packed, const void *pos_packed, int64_t n_users, float *s_pos, void *stream) {
+    int rc = sml_check_device();
+    if (rc) return rc;
+    if (n_users <= 0) return SML_OK;
+    SML_REQUIRE(users_packed && pos_packed && s_pos, SML_E_BADARG, "sml_fullcat_pos_scores: null pointer");
+    rc = fullcat_attr();
+    if (rc) return rc;
+    const int64_t ut = (n_users + 127) / 128;
+    SML_REQUIRE(ut <= 65535, SML_E_UNSUPPORTED, "sml_fullcat_pos_scores: at most 65535*128 users per call");
+    k_fullcat_rank<1><<<dim3(1, (unsigned)ut), FC_THREADS, FC_SMEM, (cudaStream_t)stream>>>(
+        (const uint8_t *)users_packed, (const uint8_t *)pos_packed, nullptr, nullptr, n_users, ut * 128, 0, 1, nullptr, nullptr, s_pos, FcTopk{});
+    SML_LAUNCH_OK();
+    return SML_OK;
+}
+
+static int64_t topk_splits(int64_t ut, int64_t it) {
+    // enough CTAs to cover the SMs twice, at most 8 item ranges per user tile (the merge scans 2 * splits * K candidates per user)
+    const int sms = sml_sm_count();
+    int64_t splits = (2 * sms + ut - 1) / ut;
+    if (splits > 8) splits = 8;
+    if (splits < 1) splits = 1;
+    if (splits > it) splits = it;
+    return splits;
+}
+
+size_t sml_fullcat_topk_workspace_bytes(int64_t n_users, int64_t n_items, int k) {
+    if (n_users <= 0 || n_items <= 0 || k <= 0) return 0;
+    const int64_t ut = (n_users + 127) / 128, it = (n_items + 127) / 128;
+    const size_t lists = (size_t)ut * topk_splits(ut, it) * 256;
+    return lists * k * (sizeof(float) + sizeof(int64_t)) + lists * sizeof(int) + 512;
+}
+
+int sml_fullcat_topk(const void *users_packed, const void *items_packed, const int64_t *exclude_id, int64_t n_users, int64_t n_items,
+                     int64_t item_id0, int k, float *out_scores, int64_t *out_ids, void *workspace, size_t workspace_bytes, void *stream) {
+    int rc = sml_check_device();
+    if (rc) return rc;
+    if (n_users <= 0) return SML_OK;
+    SML_REQUIRE(users_packed && items_packed && out_scores && out_ids && n_items > 0, SML_E_BADARG, "sml_fullcat_topk: bad arguments");
+    SML_REQUIRE(k >= 1 && k <= 64, SML_E_UNSUPPORTED, "sml_fullcat_topk: k must be in 1..64 (got %d)", k);
+    SML_REQUIRE(workspace && workspace_bytes >= sml_fullcat_topk_workspace_bytes(n_users, n_items, k), SML_E_WORKSPACE,
+                "sml_fullcat_topk: workspace too small");
+    rc = fullcat_attr();
+    if (rc) return rc;
+    const int64_t ut = (n_users + 127) / 128, it = (n_items + 127) / 128;
+    SML_REQUIRE(ut <= 65535, SML_E_UNSUPPORTED, "sml_fullcat_topk: at most 65535*128 users per call");
+    const int64_t splits = topk_splits(ut, it);
+    const int64_t per = (it + splits - 1) / splits;
+    const size_t lists = (size_t)ut * splits * 256;
+    FcTopk T;
+    char *p = (char *)workspace;
+    T.ids = (int64_t *)p; p += lists * k * sizeof(int64_t);
+    T.scores = (float *)p; p += lists * k * sizeof(float);
+    T.counts = (int *)p;
+    T.K = k;
+    k_fullcat_rank<2><<<dim3((unsigned)splits, (unsigned)ut), FC_THREADS, FC_SMEM, (cudaStream_t)stream>>>(
+        (const uint8_t *)users_packed, (const uint8_t *)items_packed, nullptr, exclude_id, n_users, n_items, item_id0, (int)per, nullptr, nullptr,
+        nullptr, T);
+    SML_LAUNCH_OK();
+    const int64_t threads = n_users * 32;
+    k_fullcat_topk_merge<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(T, (int)splits, n_users, out_scores, out_ids);
     SML_LAUNCH_OK();
     return SML_OK;
 }

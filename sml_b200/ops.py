@@ -231,9 +231,12 @@ def fullcat_ranks(user_tab, item_tab, users, pos_items, items_packed=None, item_
     positive scores when the positive item rows are not in ``item_tab`` (row-sharded catalog); ``pos_items`` are then ids
     in the shard's numbering (or -1: positive not in this shard)."""
     n = users.numel()
-    if s_pos is None:
-        s_pos = pair_scores(user_tab, item_tab, users, pos_items)
     up = pack_rows(user_tab, users)
+    if s_pos is None:
+        # the positive's score through the same tcgen05 3xTF32 arithmetic as the catalog scores: ties are exact
+        s_pos = torch.empty(n, dtype=torch.float32, device=users.device)
+        pp = pack_rows(item_tab, pos_items)
+        check(lib().sml_fullcat_pos_scores(ptr(up), ptr(pp), n, ptr(s_pos), stream()), "fullcat_pos_scores")
     if items_packed is None:
         items_packed = pack_rows(item_tab)
         n_items = item_tab.shape[0]
@@ -243,6 +246,31 @@ def fullcat_ranks(user_tab, item_tab, users, pos_items, items_packed=None, item_
     check(lib().sml_fullcat_rank(ptr(up), ptr(items_packed), ptr(s_pos), ptr(_i64(pos_items, "pos_items")), n, n_items, item_id0,
                                  ptr(gt), ptr(eq), stream()), "fullcat_rank")
     return gt, eq
+
+
+def fullcat_pos_scores(user_rows, pos_rows):
+    """[n, 64] user rows x [n, 64] item rows -> the n pair scores, computed by the full-catalog score GEMM's own arithmetic."""
+    n = user_rows.shape[0]
+    s = torch.empty(n, dtype=torch.float32, device=user_rows.device)
+    up, pp = pack_rows(user_rows), pack_rows(pos_rows)          # both operands alive until the launch is enqueued
+    check(lib().sml_fullcat_pos_scores(ptr(up), ptr(pp), n, ptr(s), stream()), "fullcat_pos_scores")
+    return s
+
+
+def fullcat_topk(user_tab, item_tab, users, k, items_packed=None, item_id0=0, n_items=None, exclude=None):
+    """Full-catalog top-k: for every id of ``users`` the k (<= 64) highest-scoring items of ``item_tab`` (or of a pre-packed
+    shard): (scores [n, k] descending, ids [n, k] int64).  ``exclude``: optional int64 [n] item id to skip per user."""
+    n = users.numel()
+    up = pack_rows(user_tab, users)
+    if items_packed is None:
+        items_packed = pack_rows(item_tab)
+        n_items = item_tab.shape[0]
+    scores = torch.empty(n, k, dtype=torch.float32, device=users.device)
+    ids = torch.empty(n, k, dtype=torch.int64, device=users.device)
+    ws = _workspace(lib().sml_fullcat_topk_workspace_bytes(n, n_items, k), users.device, "fullcat_topk")
+    check(lib().sml_fullcat_topk(ptr(up), ptr(items_packed), ptr(exclude if exclude is None else _i64(exclude, "exclude")), n, n_items, item_id0,
+                                 k, ptr(scores), ptr(ids), ptr(ws), ws.numel(), stream()), "fullcat_topk")
+    return scores, ids
 
 
 def philox_negatives(users, item_all, keys, span, seed, offset=0):

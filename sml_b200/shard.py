@@ -372,7 +372,7 @@ class ShardedSML(object):
     def eval_fullcat(self, pairs, topK, chunk=1 << 16):
         """Full-catalog recall / NDCG@K (BASELINE.json config 5) of this rank's slice of evaluated (user, positive item)
         pairs against the WHOLE row-sharded catalog: user rows and positive-item rows come through the exchange, the
-        positive score is computed once (fp32 FFMA, ops.pair_scores), every rank ranks all pairs against its own item
+        positive score is computed once (ops.fullcat_pos_scores: the score GEMM's own arithmetic), every rank ranks all pairs against its own item
         shard with the tcgen05 score GEMM (ops.fullcat_ranks) and the per-pair counts add up with one all-reduce.
         Returns global (hits, ndcg_sum, n) like eval_candidates."""
         ops = self.ops
@@ -395,7 +395,7 @@ class ShardedSML(object):
             ur = self.ex.fetch(self.ex.plan(users), lambda loc: self.user[loc])
             pr = self.ex.fetch(self.ex.plan(pos), lambda loc: self.item[loc])
             ar = torch.arange(m, dtype=torch.int64, device=dev)
-            sp = ops.pair_scores(ur.contiguous(), pr.contiguous(), ar, ar) if m else torch.empty(0, device=dev)
+            sp = ops.fullcat_pos_scores(ur.contiguous(), pr.contiguous()) if m else torch.empty(0, device=dev)
             if W > 1:       # every rank ranks every pair of the chunk against its own item shard
                 pad_u = torch.zeros(mmax, 64, device=dev); pad_u[:m] = ur
                 pad_s = torch.full((mmax,), float("inf"), device=dev); pad_s[:m] = sp

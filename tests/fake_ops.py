@@ -140,6 +140,10 @@ def run_mf_grads(a, d_rows=None, scores=None):
 
 
 # ---- full-catalog evaluation stand-ins (ShardedSML.eval_fullcat) -------------------------------------------
+def fullcat_pos_scores(user_rows, pos_rows):
+    return (user_rows * pos_rows).sum(-1)
+
+
 def pair_scores(user_tab, item_tab, user, item, norm=False):
     return (user_tab[user] * item_tab[item]).sum(-1)
 
