@@ -144,20 +144,38 @@ k_fullcat_rank(const uint8_t *__restrict__ Upk, const uint8_t *__restrict__ Ipk,
                     for (int i = 0; i < 32; ++i)
                         if (c0 + i == r && live && j == 0) diag_out[u] = v[i];
                 } else if (MODE == 0) {
+                    const int64_t first = item0 + c0;
+                    // a chunk that lies inside the catalog and does not hold the positive itself (all but one or two per row): two
+                    // compares per score -- !(s <= sp) is "greater, or NaN" (NaN ranks highest), s == sp never holds for NaN
+                    const bool plain = !sp_nan && (first + 32 - item_id0) <= n_items && (pid < first || pid >= first + 32);
+                    if (plain) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int64_t it = item0 + c0 + i;
-                        const bool ok = (it - item_id0) < n_items && it != pid;
-                        const bool vn = v[i] != v[i];
-                        c_gt += ok && ((v[i] > sp) || (vn && !sp_nan));
-                        c_eq += ok && ((v[i] == sp) || (vn && sp_nan));
+                        for (int i = 0; i < 32; ++i) { c_gt += !(v[i] <= sp); c_eq += (v[i] == sp); }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int64_t it = first + i;
+                            const bool ok = (it - item_id0) < n_items && it != pid;
+                            const bool vn = v[i] != v[i];
+                            c_gt += ok && ((v[i] > sp) || (vn && !sp_nan));
+                            c_eq += ok && ((v[i] == sp) || (vn && sp_nan));
+                        }
                     }
                 } else {
+                    // hot path: one compare per score against the list's current minimum (NaN fails `<=` and is taken: it ranks
+                    // highest, like torch.topk); only a chunk that holds a candidate, the excluded item or the end of the catalog
+                    // goes through the per-element path
+                    bool any = false;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int64_t it = item0 + c0 + i;
-                        const float sc = (v[i] != v[i]) ? INFINITY : v[i];               // NaN ranks highest, like torch.topk
-                        if (live && (it - item_id0) < n_items && it != pid && (cnt < T.K || sc > thr)) {
+                    for (int i = 0; i < 32; ++i) any |= !(v[i] <= thr);
+                    const int64_t first = item0 + c0;
+                    if (live && any) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {                                   // (unrolled: v[] must stay in registers)
+                            if (v[i] <= thr) continue;
+                            const int64_t it = first + i;
+                            if ((it - item_id0) >= n_items || it == pid) continue;
+                            const float sc = (v[i] != v[i]) ? INFINITY : v[i];
                             if (cnt < T.K) {
                                 lsc[cnt] = sc; lid[cnt] = it; ++cnt;
                             } else {
@@ -326,9 +344,10 @@ int sml_fullcat_pos_scores(const void *users_packed, const void *pos_packed, int
 }
 
 static int64_t topk_splits(int64_t ut, int64_t it) {
-    // enough CTAs to cover the SMs twice, at most 8 item ranges per user tile (the merge scans 2 * splits * K candidates per user)
+    // as few item ranges per user tile as still fill the SMs (every list pays ~K ln(items per list / K) insertions while it warms
+    // up, which is what a small catalog spends its time on), at most 8 (the merge scans 2 * splits * K candidates per user)
     const int sms = sml_sm_count();
-    int64_t splits = (2 * sms + ut - 1) / ut;
+    int64_t splits = (sms + ut - 1) / ut;
     if (splits > 8) splits = 8;
     if (splits < 1) splits = 1;
     if (splits > it) splits = it;

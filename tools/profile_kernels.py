@@ -37,6 +37,27 @@ def main():
             ("transfer_forward 59082 rows", lambda: ops.transfer_forward(lu, hu, tr.theta[:ops.NET_STRIDE], out=out), U * 403456 / 1e12, "TFLOP"),
             ("mf_step B=1024", lambda: ops.mf_step(a), 1024, "triples"),
             ("fullcat_rank 16384 users x 122816 items", lambda: ops.fullcat_ranks(hu, hi, eu, ep, items_packed=ipk, n_items=I), 16384 * I * 128 / 1e12, "TFLOP")]
+    # round 2 additions: fused transfer forward, fused plain-MF step, row-lazy Adam, owner-side exchange kernels, top-k
+    big = 1_000_000
+    a1, b1, o1 = R(big, 64), R(big, 64), torch.empty(big, 64, device=dev)
+    work.append(("transfer_fused 1M rows", lambda: ops.transfer_forward(a1, b1, tr.theta[:ops.NET_STRIDE], out=o1), big * 403456 / 1e12, "TFLOP"))
+    st = ops.new_adam_state(dev, history=True)
+    pu, pi = R(2_000_000, 64), R(2_000_000, 64)
+    mu, vu, mi, vi = z(pu), z(pu), z(pi), z(pi)
+    su, si = ops.new_row_stamps(2_000_000, st), ops.new_row_stamps(2_000_000, st)
+    hd_u, hd_i = ops.new_list_heads(2_000_000, dev), ops.new_list_heads(2_000_000, dev)
+    Bp = 65536
+    pu_ids = [torch.randint(0, 2_000_000, (Bp,), generator=g).to(dev) for _ in range(3)]
+    work.append(("plain_mf_step 65536 triples (exact dense Adam, row-lazy)",
+                 lambda: ops.plain_mf_step(pu, pi, mu, vu, mi, vi, hd_u, hd_i, pu_ids[0], pu_ids[1], pu_ids[2], st, 0.01, loss, loss=ops.LOSS_BPR,
+                                           optimizer=ops.OPT_ADAM_DENSE_EXACT, stamp_user=su, stamp_item=si), Bp * 4632 / 1e9, "GB"))
+    work.append(("adam_flush 2M rows", lambda: ops.adam_flush(pu, mu, vu, su, st), 2_000_000 * 6 * 256 / 1e9, "GB"))
+    loc = torch.randint(0, U, (24576,), generator=g).to(dev)
+    drow = R(24576, 64)
+    gtab = z(hu)
+    work.append(("gather_pairs 24576 rows", lambda: ops.gather_pairs(lu, hu, loc), 24576 * 1024 / 1e9, "GB"))
+    work.append(("scatter_grads 24576 rows", lambda: ops.scatter_grads(gtab, hu, loc, drow, 1.0, 1e-6), 24576 * 768 / 1e9, "GB"))
+    work.append(("fullcat_topk 16384 users x 122816 items, K=20", lambda: ops.fullcat_topk(hu, hi, eu, 20, items_packed=ipk, n_items=I), 16384 * I * 128 / 1e12, "TFLOP"))
     for name, fn, units, unit in work:
         fn(); torch.cuda.synchronize()
         if os.environ.get("SML_TIME"):
