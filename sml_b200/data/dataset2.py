@@ -109,6 +109,15 @@ class transfer_data(object):
             self._cache.pop(next(iter(self._cache)))
         return hit
 
+    def peek_files(self, d_time):
+        """Files of stage ``d_time`` that are ALREADY in the host cache (no disk I/O here: reading a 600 MB file would stall the
+        host while it should be enqueueing kernels); meta_train uploads them ahead of time."""
+        now_time = self.online_trian_time + d_time
+        if (now_time + 1) >= self.len:
+            return []
+        names = [("test", self.file_list[now_time]), ("test", self.file_list[now_time + 1])]
+        return [self._cache[k] for k in names if k in self._cache]
+
     def _set_t(self, now_time):
         if self.MF_sample == "alone":
             return self._load("train", self.file_list[now_time])

@@ -35,3 +35,10 @@ class MemoryStream(object):
         if self.TR_stop_:
             return set_t, None, now_test, now_test
         return set_t, self.periods[now + 1][0], now_test, val
+
+    def peek_files(self, d_time):
+        """The test-format files stage ``d_time`` will read (set_t, val), without side effects: what meta_train uploads ahead of time."""
+        now = self.online_trian_time + d_time
+        if now + 1 >= self.len:
+            return []
+        return [self.periods[now][1], self.periods[now + 1][1]]

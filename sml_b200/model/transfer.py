@@ -191,6 +191,8 @@ class meta_train(object):
         self._ws = {}
         self._dev_cache = {}
         self.dev_cache_cap = 6                     # period files kept resident on the device
+        self.prefetch = os.environ.get("SML_PREFETCH", "1") != "0"   # upload the next period's files during the current one (prefetch_files)
+        self._copy_stream = None
         # one CUDA graph per (loop kind, epoch length, batch size, lr, l2): an epoch is ~10^3 short kernels, and the
         # host cannot enqueue them as fast as the GPU retires them (tools/epoch_bench.py: 104 us/step of launch time
         # against 119 us/step of kernel time for the transfer loop), so epochs after the first are graph replays
@@ -227,16 +229,42 @@ class meta_train(object):
         return self._ws[B]
 
     def _to_device(self, arr):
-        """numpy int array -> cached int64 device tensor (period files are re-used across stages)."""
+        """numpy int array -> cached int64 device tensor (period files are re-used across stages: D_{t+1} is the validation
+        file of period t and the training file of period t+1, so every file crosses PCIe once)."""
         key = id(arr)
         hit = self._dev_cache.get(key)
         if hit is not None and hit[0] is arr:
+            if hit[2] is not None:                       # uploaded ahead of time on the copy stream (prefetch_files)
+                torch.cuda.current_stream().wait_event(hit[2])
+                hit[1].record_stream(torch.cuda.current_stream())     # allocated on the copy stream, used on this one
+                self._dev_cache[key] = (arr, hit[1], None)
             return hit[1]
         t = torch.from_numpy(np.ascontiguousarray(arr)).to(self.device, dtype=torch.int64, non_blocking=False)
-        if len(self._dev_cache) > self.dev_cache_cap:
-            self._dev_cache.pop(next(iter(self._dev_cache)))
-        self._dev_cache[key] = (arr, t)
+        self._cache_put(key, arr, t, None)
         return t
+
+    def _cache_put(self, key, arr, t, event):
+        while len(self._dev_cache) > self.dev_cache_cap:
+            self._dev_cache.pop(next(iter(self._dev_cache)))
+        self._dev_cache[key] = (arr, t, event)
+
+    def prefetch_files(self, arrs):
+        """Start the host->device copy of period files that a LATER stage will need, on a side stream, so that the
+        transfer overlaps the current period's kernels (pinned host arrays copy asynchronously; pageable ones are staged
+        by the driver and still overlap the GPU work already enqueued)."""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        for arr in arrs:
+            if arr is None or (id(arr) in self._dev_cache and self._dev_cache[id(arr)][0] is arr):
+                continue
+            src = torch.from_numpy(np.ascontiguousarray(arr))
+            if src.dtype != torch.int64:
+                src = src.to(torch.int64)
+            with torch.cuda.stream(self._copy_stream):
+                t = src.to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            self._cache_put(id(arr), arr, t, ev)
 
     def _sample_dataset(self, arr):
         """SampleDaset(set_tt) is stateless (its draws come from the global numpy generator), so the
@@ -516,6 +544,9 @@ class meta_train(object):
         set_t, set_tt, now_test, val = self.get_next_data(stage_id)
         if set_t is None:
             return False
+        if self.prefetch and self.device.type == "cuda" and hasattr(self.dataset, "peek_files"):
+            # this stage's files first (in the order they are used), then the next stage's: their upload overlaps this period
+            self.prefetch_files([set_t, val, now_test] + list(self.dataset.peek_files(stage_id + 1)))
         if now_test is None:                       # online training, no real test yet (:772-792)
             for phase in range(args.multi_num):
                 self.MF_train_onestage(args, set_t, stage_id, val=val)
