@@ -35,6 +35,15 @@ int sml_use_fused_fwd() {
     return v;
 }
 
+int sml_use_fused_fc2() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SML_FUSE_FC2");
+        v = (e && strcmp(e, "0") == 0) ? 0 : 1;
+    }
+    return v;
+}
+
 int sml_use_pdl() {
     static int v = -1;
     if (v < 0) {

@@ -188,7 +188,7 @@ int sml_launch_loss(const float *Y, const float *rowsq, int64_t B, int64_t row_p
                     float adaptive = 0.f);       // --need_adaptive: + adaptive * sum_b ||x_hat user row b|| (needs rowsq)
 
 // tcgen05 GEMM with pre-packed operands (umma_packed.cu)
-enum { SML_PK_FC1 = 0, SML_PK_FC2 = 1, SML_PK_D2 = 2, SML_PK_D1 = 3 };
+enum { SML_PK_FC1 = 0, SML_PK_FC2 = 1, SML_PK_D2 = 2, SML_PK_D1 = 3, SML_PK_FC1_FC2 = 4 };
 struct SmlPkProb {
     const uint8_t *A;     // packed A, 128-row tiles
     const uint8_t *B;     // packed B (weights), BN-row tiles
@@ -205,6 +205,11 @@ struct SmlPkProb {
     uint8_t *Cpk;         // packed output = A operand of the next GEMM (K = N), or null
     int c_tile0;
     float *colsum;        // d2 only: += column sums of the valid output rows (fc1 bias gradient), or null
+    // SML_PK_FC1_FC2 only: fc2 fused into the fc1 tiles
+    const uint8_t *B2;    // packed W2 (P2 operand, 64-row blocks)
+    const float *bias2;   // [64]
+    float *Y;             // plain fc2 output [rows][ldy], zeroed by the caller (the tiles add their partial products)
+    int ldy;
 };
 int sml_launch_umma_packed(const SmlPkProb *probs, int n_probs, int epi, cudaStream_t st, int ksplit = 1);
 // packed weight operands of the nets: per net SML_PK_THETA_BYTES
@@ -227,3 +232,5 @@ int sml_launch_transfer_fused(const float *x_t, const float *x_hat, const int64_
                               const float *theta_net, const uint8_t *wpk, int normalize_out, float *out, cudaStream_t st);
 // 1 = sml_transfer_fwd uses the fused kernel (default); SML_FUSED_FWD=0 or sml_debug_set_mask(2048) select the three-kernel path
 int sml_use_fused_fwd();
+// 1 = the step forward fuses fc2 into the fc1 tiles (default); SML_FUSE_FC2=0 or sml_debug_set_mask(4096) keep two launches
+int sml_use_fused_fc2();

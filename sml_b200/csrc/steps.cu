@@ -112,6 +112,7 @@ void pk_pair(SmlPkProb out[2], const Rows &r, const uint8_t *A, int KC, size_t w
         p.N = N;
         p.bias = bias_off ? theta + (size_t)net * SML_NET_STRIDE + bias_off : nullptr;
         p.aux = aux; p.C = C; p.ldc = ldc; p.Cpk = Cpk; p.c_tile0 = p.a_tile0; p.colsum = nullptr;
+        p.B2 = nullptr; p.bias2 = nullptr; p.Y = nullptr; p.ldy = 0;
     }
 }
 
@@ -169,7 +170,10 @@ int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, b
     float *gbu2 = (tc && g_theta) ? g_theta + SML_OFF_F2B : nullptr, *gbi2 = (tc && g_theta) ? g_theta + SML_NET_STRIDE + SML_OFF_F2B : nullptr;
     // split-K slices accumulate into Y (fc2) and dA (d1): the conv prologue and the loss kernel clear the batch rows on their
     // way (a memset node in the chain would cost a launch and break the programmatic-dependent-launch overlap)
-    const bool zero_y = tc && step_ksplit(r, 0) > 1, zero_dA = tc && step_ksplit(r, 1) > 1;
+    // fc2 fused into the fc1 tiles (umma_packed.cu, SML_PK_FC1_FC2) when the batch is a handful of row tiles (the 768-row transfer
+    // step: 70.8 -> 68.0 us; at 3 072 rows the 128 x 128 fc1 tiles + a separate fc2 are faster: 84.6 vs 92.1 us)
+    const bool fuse_fc2 = tc && sml_use_fused_fc2() && (r.user_tiles + r.item_tiles) <= 12 && !(sml_debug_mask() & (128 | 4096));
+    const bool zero_y = tc && (fuse_fc2 || step_ksplit(r, 0) > 1), zero_dA = tc && step_ksplit(r, 1) > 1;
     rc = sml_launch_conv_fwd(g, 3, a->variant, (!tc || need_plain_A) ? w.A : nullptr, tc ? w.Apk : nullptr,
                              want_rowsq ? w.rowsq : nullptr, st, zero_y ? w.Y : nullptr);
     if (rc) return rc;
@@ -179,13 +183,25 @@ int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, b
         SmlPkProb p[2];
         // fc1: Z1 = A W1^T + b1 (conv_transfer.py:47); also emits GELU(Z1) packed for fc2
         pk_pair(p, r, w.Apk, 10, SML_PK_OFF_P1, 512, a->theta, SML_OFF_F1B, nullptr, w.Z1, 512, w.Gpk, w.theta_pk);
-        rc = sml_launch_umma_packed(p, 2, SML_PK_FC1, st);
-        if (rc) return rc;
-        if (sml_debug_mask() & 128) return SML_OK;
-        // fc2: Y = GELU(Z1) W2^T + b2 (:48-49)
-        pk_pair(p, r, w.Gpk, 16, SML_PK_OFF_P2, 64, a->theta, SML_OFF_F2B, nullptr, w.Y, 64, nullptr, w.theta_pk);
-        rc = sml_launch_umma_packed(p, 2, SML_PK_FC2, st, step_ksplit(r, 0));
-        if (rc) return rc;
+        if (fuse_fc2) {
+            // fc1 + fc2 in one launch: every 128 x 64 fc1 tile multiplies its GELU(Z1) tile with its K slice of W2 and adds into Y
+            for (int net = 0; net < 2; ++net) {
+                p[net].Cpk = nullptr;
+                p[net].B2 = w.theta_pk + net * SML_PK_THETA_BYTES + SML_PK_OFF_P2;
+                p[net].bias2 = a->theta + (size_t)net * SML_NET_STRIDE + SML_OFF_F2B;
+                p[net].Y = w.Y; p[net].ldy = 64;
+            }
+            rc = sml_launch_umma_packed(p, 2, SML_PK_FC1_FC2, st);
+            if (rc) return rc;
+        } else {
+            rc = sml_launch_umma_packed(p, 2, SML_PK_FC1, st);
+            if (rc) return rc;
+            if (sml_debug_mask() & 128) return SML_OK;
+            // fc2: Y = GELU(Z1) W2^T + b2 (:48-49)
+            pk_pair(p, r, w.Gpk, 16, SML_PK_OFF_P2, 64, a->theta, SML_OFF_F2B, nullptr, w.Y, 64, nullptr, w.theta_pk);
+            rc = sml_launch_umma_packed(p, 2, SML_PK_FC2, st, step_ksplit(r, 0));
+            if (rc) return rc;
+        }
     } else {
         SmlGemmProb fc1[2] = {
             {w.A, tu + SML_OFF_F1W, tu + SML_OFF_F1B, nullptr, w.Z1, (int)B, 512, 320, 320, 320, 512},
@@ -399,10 +415,10 @@ int sml_transfer_fwd(const float *x_t, const float *x_hat, const int64_t *ids, i
         if (rc) return rc;
         if (tc) {
             const int tiles = (int)(up128(n) / 128);
-            SmlPkProb f1 = {Apk, theta_pk + SML_PK_OFF_P1, 10, tiles, 0, 0, (int)n, 512, theta_net + SML_OFF_F1B, nullptr, nullptr, 512, Gpk, 0, nullptr};
+            SmlPkProb f1 = {Apk, theta_pk + SML_PK_OFF_P1, 10, tiles, 0, 0, (int)n, 512, theta_net + SML_OFF_F1B, nullptr, nullptr, 512, Gpk, 0, nullptr, nullptr, nullptr, nullptr, 0};
             rc = sml_launch_umma_packed(&f1, 1, SML_PK_FC1, st);
             if (rc) return rc;
-            SmlPkProb f2 = {Gpk, theta_pk + SML_PK_OFF_P2, 16, tiles, 0, 0, (int)n, 64, theta_net + SML_OFF_F2B, nullptr, out + r0 * SML_D, 64, nullptr, 0, nullptr};
+            SmlPkProb f2 = {Gpk, theta_pk + SML_PK_OFF_P2, 16, tiles, 0, 0, (int)n, 64, theta_net + SML_OFF_F2B, nullptr, out + r0 * SML_D, 64, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0};
             rc = sml_launch_umma_packed(&f2, 1, SML_PK_FC2, st);
             if (rc) return rc;
         } else {

@@ -92,21 +92,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-template <int BN> struct PkSmem {
+template <int BN, bool FUSE = false> struct PkSmem {
     static constexpr uint32_t A_BYTES = pk_block_bytes(128), B_BYTES = pk_block_bytes(BN);
     static constexpr uint32_t STAGE = A_BYTES + B_BYTES;
-    static constexpr uint32_t TOTAL = PKG_STAGES * STAGE + 64;
+    static constexpr uint32_t W2_BYTES = FUSE ? 2 * pk_block_bytes(64) : 0;      // fused fc2: this CTA's 64-wide K slice of W2 (2 chunks)
+    static constexpr uint32_t TOTAL = PKG_STAGES * STAGE + W2_BYTES + 128;
 };
 
 // BROWS = rows per block of the packed B operand in memory.  BROWS == BN: one bulk copy per block.  BROWS = 128 with BN = 64
 // (small batches: twice the CTAs, each pulling less through its SM's L2 port and running half the epilogue): the 64 rows
 // of a tile are 8 consecutive 8-row groups inside the hi half and inside the lo half of a 128-row block, i.e. two copies.
-template <int BN, int EPI, int BROWS = BN>
+// FUSE (fc1 only, BN = 64): the CTA goes on to multiply its 128 x 64 tile of GELU(Z1) -- kept in shared memory as the next
+// A operand instead of being written to HBM in packed form -- with the matching 64-wide K slice of W2 and adds the partial
+// Y[128 x 64] into the (pre-zeroed) fc2 output with fp32 atomics: fc1 and fc2 in one launch, an 8-way split-K fc2.
+template <int BN, int EPI, int BROWS = BN, bool FUSE = false>
 __global__ void __launch_bounds__(PKG_THREADS, 1)
 k_umma_packed(PkParams P) {
     static_assert(BROWS == BN || (BROWS == 128 && BN == 64), "unsupported packed-B block shape");
+    static_assert(!FUSE || (EPI == SML_PK_FC1 && BN == 64), "fc2 can only be fused into the 128 x 64 fc1 tiles");
     extern __shared__ __align__(128) uint8_t smem[];
-    using S = PkSmem<BN>;
+    using S = PkSmem<BN, FUSE>;
     // split-K: blockIdx.z = problem * ksplit + slice.  A single CTA streaming K = 512 pulls 0.6 MB through one SM's
     // L2 port (~7 us); slicing K spreads that over more SMs.  Slices add their partial tile with fp32 atomics into a
     // pre-zeroed C (plain-output epilogues only); slice 0 adds the bias.
@@ -118,19 +123,23 @@ k_umma_packed(PkParams P) {
     const int c_beg = ks * c_per, c_end = (c_beg + c_per < p.KC) ? c_beg + c_per : p.KC;
     if (c_beg >= c_end) return;
     const bool split = P.ksplit > 1;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + S::TOTAL - 64);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + S::TOTAL - 128);
     uint64_t *empty = full + PKG_STAGES;
     uint64_t *done = empty + PKG_STAGES;
+    uint64_t *w2_full = done + 1, *g_full = done + 2, *y_done = done + 3;          // fused fc2 only
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::TOTAL - 8);
+    uint8_t *w2s = smem + PKG_STAGES * S::STAGE;                                    // W2 slice (fused fc2)
+    constexpr int TMEM_COLS = FUSE ? 512 : BN * PKG_NACC;                           // + 64 columns for the partial Y
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < PKG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(done, 1);
+        if (FUSE) { mbar_init(w2_full, 1); mbar_init(g_full, PKG_EPI_THREADS); mbar_init(y_done, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN * PKG_NACC) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -146,6 +155,10 @@ k_umma_packed(PkParams P) {
             const uint8_t *a = p.A + (size_t)(p.a_tile0 + tile_m) * KC * S::A_BYTES;
             constexpr uint32_t B_SRC = pk_block_bytes(BROWS);
             const uint8_t *b = p.B + (size_t)(tile_n * BN / BROWS) * KC * B_SRC + (size_t)((tile_n * BN) % BROWS / 8) * PK_SBO;
+            if (FUSE) {     // W2[:, 64 tile_n .. +64) as two 64-row blocks of the packed P2 operand: needed only after the main loop
+                mbar_expect_tx(w2_full, S::W2_BYTES);
+                bulk_g2s(w2s, p.B2 + (size_t)(2 * tile_n) * pk_block_bytes(64), S::W2_BYTES, w2_full);
+            }
             for (int c = c_beg; c < c_end; ++c) {
                 const int i = c - c_beg, s = i % PKG_STAGES;
                 if (i >= PKG_STAGES) mbar_wait(&empty[s], ((i / PKG_STAGES) - 1) & 1);
@@ -189,6 +202,30 @@ k_umma_packed(PkParams P) {
         }
         if (leader) umma_commit(done);
         __syncwarp();
+        if (FUSE) {
+            // fc2 partial: Y[128 x 64] = GELU(Z1)[128 x 64 of this tile] W2[:, slice]^T, A operand written by the epilogue warps
+            constexpr uint32_t ID64 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            mbar_wait(w2_full, 0);
+            mbar_wait(g_full, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t ga = smem_u32(smem), wb = smem_u32(w2s);
+            auto dlo = [](uint32_t a) { return ((a >> 4) & 0x3FFF) | ((PK_LBO >> 4) << 16); };
+            if (leader) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const uint32_t a_hi = dlo(ga + c * pk_block_bytes(128)), a_lo = dlo(ga + c * pk_block_bytes(128) + pk_half_bytes(128));
+                    const uint32_t b_hi = dlo(wb + c * pk_block_bytes(64)), b_lo = dlo(wb + c * pk_block_bytes(64) + pk_half_bytes(64));
+#pragma unroll
+                    for (int k = 0; k < PK_BK / 8; ++k) {
+                        umma_tf32_h(tmem + BN * PKG_NACC, a_lo + k * KSTEP, b_hi + k * KSTEP, DHI, ID64, (c | k) != 0);
+                        umma_tf32_h(tmem + BN * PKG_NACC, a_hi + k * KSTEP, b_lo + k * KSTEP, DHI, ID64, 1);
+                        umma_tf32_h(tmem + BN * PKG_NACC, a_hi + k * KSTEP, b_hi + k * KSTEP, DHI, ID64, 1);
+                    }
+                }
+                umma_commit(y_done);
+            }
+            __syncwarp();
+        }
     } else {
         // ===== epilogue warps: straight from TMEM registers, one accumulator row per thread =====
         mbar_wait(done, 0);
@@ -259,11 +296,13 @@ k_umma_packed(PkParams P) {
                     for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                 }
             }
-            if ((EPI == SML_PK_FC1 || EPI == SML_PK_D2) && p.Cpk) {
+            if ((EPI == SML_PK_FC1 || EPI == SML_PK_D2) && (p.Cpk || FUSE)) {
                 // column nb.. of this GEMM = K index of the next one: one 32-wide K chunk, 8 quads; lanes r%8
                 // are 16 B apart => every store instruction writes whole 128 B core matrices
-                uint8_t *blk = p.Cpk + ((size_t)(p.c_tile0 + tile_m) * (p.N / PK_BK) + (nb >> 5)) * pk_block_bytes(128) +
-                               (uint32_t)(r >> 3) * PK_SBO + (uint32_t)(r & 7) * 16;
+                // (fused fc2: the chunk goes to shared memory -- the pipeline stages are free once `done` has fired)
+                uint8_t *blk = FUSE ? smem + (size_t)(c0 >> 5) * pk_block_bytes(128) + (uint32_t)(r >> 3) * PK_SBO + (uint32_t)(r & 7) * 16
+                                    : p.Cpk + ((size_t)(p.c_tile0 + tile_m) * (p.N / PK_BK) + (nb >> 5)) * pk_block_bytes(128) +
+                                          (uint32_t)(r >> 3) * PK_SBO + (uint32_t)(r & 7) * 16;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     float h[4], l[4];
@@ -278,9 +317,27 @@ k_umma_packed(PkParams P) {
             }
         }
     }
+    if (FUSE && warp >= 2) {
+        // hand the GELU(Z1) tile to the tensor core, then add the partial fc2 product into Y
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(g_full)) : "memory");
+        mbar_wait(y_done, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int quarter = warp & 3, chalf = (warp - 2) >> 2;
+        const int r = quarter * 32 + lane;
+        const int64_t m = p.row0 + (int64_t)tile_m * 128 + r;
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + BN * PKG_NACC + chalf * 32, v);
+        if (tile_m * 128 + r < p.M) {
+            float *y = p.Y + m * p.ldy + chalf * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(y + i, tile_n == 0 ? v[i] + __ldg(p.bias2 + chalf * 32 + i) : v[i]);
+        }
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN * PKG_NACC) : "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
 }
 
 // ---- theta packer ---------------------------------------------------------------------------------
@@ -327,15 +384,15 @@ __global__ void __launch_bounds__(256) k_pack_theta(const float *__restrict__ th
     }
 }
 
-template <int BN, int EPI, int BROWS = BN>
+template <int BN, int EPI, int BROWS = BN, bool FUSE = false>
 int launch_pk(const PkParams &P, dim3 grid, cudaStream_t st) {
-    auto kern = k_umma_packed<BN, EPI, BROWS>;
+    auto kern = k_umma_packed<BN, EPI, BROWS, FUSE>;
     static bool attr_set = false;
     if (!attr_set) {
-        SML_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PkSmem<BN>::TOTAL));
+        SML_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PkSmem<BN, FUSE>::TOTAL));
         attr_set = true;
     }
-    SML_CUDA_OK(sml_launch(kern, grid, dim3(PKG_THREADS), PkSmem<BN>::TOTAL, st, P));
+    SML_CUDA_OK(sml_launch(kern, grid, dim3(PKG_THREADS), PkSmem<BN, FUSE>::TOTAL, st, P));
     SML_LAUNCH_OK();
     return SML_OK;
 }
@@ -362,6 +419,11 @@ int sml_launch_umma_packed(const SmlPkProb *probs, int n_probs, int epi, cudaStr
     for (int i = 0; i < n_probs; ++i) tot_mt += probs[i].m_tiles;
     const bool narrow = tot_mt <= 12 && !(sml_debug_mask() & 512);
     switch (epi) {
+        case SML_PK_FC1_FC2:     // fc1 with fc2 fused into its epilogue (128 x 64 tiles); probs[i].B2 / bias2 / Y describe fc2
+            SML_REQUIRE(N == 512 && ksplit == 1, SML_E_BADARG, "packed gemm: fused fc1 + fc2 needs N = 512 and no split-K");
+            for (int i = 0; i < n_probs; ++i)
+                SML_REQUIRE(probs[i].B2 && probs[i].bias2 && probs[i].Y, SML_E_BADARG, "packed gemm: fused fc1 + fc2 needs B2, bias2 and Y");
+            return launch_pk<64, SML_PK_FC1, 128, true>(P, dim3(N / 64, max_mt, n_probs), st);
         case SML_PK_FC1:
             SML_REQUIRE(N % 128 == 0, SML_E_BADARG, "packed gemm: fc1 N");
             if (narrow) return launch_pk<64, SML_PK_FC1, 128>(P, dim3(N / 64, max_mt, n_probs), st);
