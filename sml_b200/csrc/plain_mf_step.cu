@@ -51,7 +51,8 @@ struct PmsParams {
     int32_t *next;        // [3B] previous occurrence of the same row in this batch, -1 = first (the owner)
     float *partials;      // [2 * gridDim.x]
     int32_t *worklist;    // [3B] first occurrences of rows that occur several times (phase 2 work)
-    unsigned int *work_count;   // [2] entries in worklist, double-buffered by step parity; zero between steps
+    unsigned int *work_count;   // [0..1] entries in worklist, double-buffered by launch parity (zero between launches); [2] launches so far
+                                // (the parity lives in the workspace, not in the Adam step: a workspace outlives optimizer states)
 };
 
 __device__ __forceinline__ float hw_sum(float v) {      // sum over the 16 lanes of a half-warp
@@ -141,7 +142,8 @@ k_plain_mf_step(PmsParams P) {
     const float invB = 1.0f / (float)P.B;
     float acc_loss = 0.f, acc_l2 = 0.f;
     const int64_t B_up = (P.B + 1) & ~(int64_t)1;          // both half-warps of a warp stay in the loop for the shuffles
-    unsigned int *work_count = P.work_count + (t & 1);
+    const unsigned int seq = __ldcg(P.work_count + 2);     // every CTA reads it before the second grid sync; it moves after that one
+    unsigned int *work_count = P.work_count + (seq & 1u);
     auto slot = [&](int buf, int j) -> float4 * { return stage + (size_t)(buf * 9 + j) * PMS_THREADS + threadIdx.x; };
     auto ids_of = [&](int64_t b, int64_t &iu, int64_t &ii, int64_t &ij) {
         const int64_t bb = b < P.B ? b : P.B - 1;          // triples past the end recompute the last one (never stored)
@@ -257,7 +259,7 @@ k_plain_mf_step(PmsParams P) {
         for (int i = 0; i < PMS_THREADS / 32; ++i) { a += s_part[i][0]; q += s_part[i][1]; }
         P.partials[2 * blockIdx.x] = a; P.partials[2 * blockIdx.x + 1] = q;
     }
-    if (tid == 0) P.work_count[(t + 1) & 1] = 0;           // the next step's counter (this step's was zeroed by the previous one)
+    if (tid == 0) P.work_count[(seq + 1u) & 1u] = 0;       // the next launch's counter (this launch's was zeroed by the previous one)
     grid.sync();
     // ---------------- phase 2: rows with several occurrences -- the first one sums the chain and applies step t ----------------
     // phase 1 listed those first occurrences; one half-warp per entry
@@ -293,6 +295,7 @@ k_plain_mf_step(PmsParams P) {
         const float loss = (P.loss_kind == SML_LOSS_BCE) ? (-(a * invB) + q) : a;
         P.loss_out[0] = loss;
         P.loss_out[1] += loss;
+        P.work_count[2] = seq + 1u;
         P.state[0] = t;                                    // every CTA read the old counter before the first grid sync
         float *f = reinterpret_cast<float *>(P.state + 1);
         f[0] = ct.x; f[1] = ct.y;

@@ -335,6 +335,42 @@ def test_plain_mf_fused_step_vs_oracle(dev, loss_kind):
     assert np.array_equal(pu.cpu().numpy()[untouched], ut[untouched])            # rows no gradient ever reached
 
 
+def test_plain_mf_fused_step_workspace_outlives_optimizer_state(dev):
+    """The scratch of sml_plain_mf_step is shared by every caller in the process.  A run that ends on an odd step with
+    duplicate ids in its last batch must not leak its duplicate-row work list into the next run, which starts a fresh Adam state
+    at step 1 with a smaller batch (the list counters are double-buffered by LAUNCH parity kept in the scratch itself)."""
+    from sml_b200 import ops
+    rng = np.random.default_rng(13)
+    z = torch.zeros_like
+
+    def fresh(U, I):
+        ut = (0.3 * rng.standard_normal((U, 64))).astype(np.float32); it = (0.3 * rng.standard_normal((I, 64))).astype(np.float32)
+        pu, pi = T(ut, dev), T(it, dev)
+        st = ops.new_adam_state(dev, history=True)
+        return dict(ut=ut, it=it, pu=pu, pi=pi, mu=z(pu), vu=z(pu), mi=z(pi), vi=z(pi), st=st, su=ops.new_row_stamps(U, st),
+                    si=ops.new_row_stamps(I, st), hu=ops.new_list_heads(U, dev), hi=ops.new_list_heads(I, dev), loss=torch.zeros(2, device=dev))
+
+    def step(s, u, i, j):
+        ops.plain_mf_step(s["pu"], s["pi"], s["mu"], s["vu"], s["mi"], s["vi"], s["hu"], s["hi"], T(u, dev), T(i, dev), T(j, dev), s["st"],
+                          0.01, s["loss"], loss=ops.LOSS_BCE, l2_u=1e-3, l2_i=1e-3, optimizer=ops.OPT_ADAM_DENSE_EXACT,
+                          stamp_user=s["su"], stamp_item=s["si"])
+    a = fresh(64, 64)
+    for _ in range(3):                                        # odd number of steps, 4 096 triples on 64 rows: every row is a duplicate
+        step(a, *(rng.integers(0, 64, 4096).astype(np.int64) for _ in range(3)))
+    b = fresh(300, 400)
+    nu, ni = b["ut"].copy(), b["it"].copy()
+    nmu, nvu, nmi, nvi = (np.zeros_like(x) for x in (nu, nu, ni, ni))
+    for s in range(4):
+        u, i, j = (rng.integers(0, n, 97).astype(np.int64) for n in (40, 60, 60))
+        lo, gu, gi = O.plain_mf_bce_grads(nu, ni, u, i, j, 1e-3, 1e-3)
+        O.adam_step(nu, gu, nmu, nvu, s + 1, 0.01); O.adam_step(ni, gi, nmi, nvi, s + 1, 0.01)
+        step(b, u, i, j)
+        assert abs(b["loss"][0].item() - float(lo)) < 1e-4 * max(1.0, abs(float(lo)))
+    ops.adam_flush(b["pu"], b["mu"], b["vu"], b["su"], b["st"]); ops.adam_flush(b["pi"], b["mi"], b["vi"], b["si"], b["st"])
+    assert np.abs(b["pu"].cpu().numpy() - nu).max() < 2e-5 and np.abs(b["pi"].cpu().numpy() - ni).max() < 2e-5
+    assert rel_err(b["mu"].cpu().numpy(), nmu) < 1e-4 and rel_err(b["vi"].cpu().numpy(), nvi) < 1e-4
+
+
 def test_plain_mf_fused_step_modes(dev):
     """(a) the fused step against the two-kernel path (sml_plain_mf_grads + dense Adam sweep); (b) when the same rows are
     touched at every step the exact and the sparse mode are the same arithmetic: bit-identical; (c) SML_OPT_ADAM_SPARSE
