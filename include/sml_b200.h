@@ -303,7 +303,7 @@ int64_t sml_host_rejection_walk_hashed(const int64_t *draws_host, int64_t n_draw
  * tcgen05 3xTF32 kernel (bn = 64 | 128, optional transposed store C[n][m]), 0 the SIMT fp32 kernel. */
 /* Profiling aid (tools/tr_breakdown.py): bit mask that drops stages of sml_tr_step / sml_mf_step so that the critical
  * path can be measured by difference.  1: no weight gradients, 2: no dA / conv backward, 4: nothing after the loss,
- * 8: nothing after fc2, 64: no optimizer update, 128: nothing after fc1, 256: nothing after the conv prologue, 512: no 128 x 64 tiles for small batches.
+ * 8: nothing after fc2, 64: no optimizer update, 128: nothing after fc1, 256: nothing after the conv prologue, 512: no 128 x 64 tiles for small batches, 2048: three-kernel transfer forward, 4096: separate fc2 launch, 8192: separate loss kernel.
  * Results are garbage unless the mask is 0 (the default) or 512.  Returns the previous mask. */
 int sml_debug_set_mask(int mask);
 int sml_debug_mask(void);

@@ -66,7 +66,8 @@ __device__ __forceinline__ void conv_point(const ConvW &w, float x0, float x1, f
 // ---------------------------------------------------------------------------------------------
 template <int R>
 __global__ void __launch_bounds__(CONV_THREADS)
-k_conv_fwd(ConvParams P, float *__restrict__ A, uint8_t *__restrict__ Apk, float *__restrict__ rowsq, float *__restrict__ zero_y) {
+k_conv_fwd(ConvParams P, float *__restrict__ A, uint8_t *__restrict__ Apk, float *__restrict__ rowsq, float *__restrict__ zero_y,
+           float *__restrict__ zero_dA) {
     __shared__ ConvW sw;
     sml_pdl_wait();
     sml_pdl_trigger();
@@ -97,6 +98,10 @@ k_conv_fwd(ConvParams P, float *__restrict__ A, uint8_t *__restrict__ Apk, float
             if (lane == 0 && h0 == 0) rowsq[g.row0 + r] = q;
         }
         if (zero_y) zero_y[(g.row0 + r) * SML_D + lane + 32 * h0] = 0.f;   // split-K fc2 accumulates into Y (no memset node in the chain)
+        if (zero_dA) {                                                       // split-K d1 accumulates into dA
+#pragma unroll
+            for (int k = 0; k < SML_FC1_IN / 2; k += 32) zero_dA[(g.row0 + r) * SML_FC1_IN + h0 * (SML_FC1_IN / 2) + k + lane] = 0.f;
+        }
         float *a = A ? A + (g.row0 + r) * SML_FC1_IN : nullptr;
 #pragma unroll
         {
@@ -374,7 +379,7 @@ int grid_for_rows(int64_t max_n) {
 }  // namespace
 
 int sml_launch_conv_fwd(const SmlRowGroup *groups, int n_groups, int variant, float *A, uint8_t *Apk, float *rowsq,
-                        cudaStream_t st, float *zero_y) {
+                        cudaStream_t st, float *zero_y, float *zero_dA) {
     SML_REQUIRE(n_groups >= 1 && n_groups <= MAX_GROUPS, SML_E_BADARG, "conv_fwd: bad group count %d", n_groups);
     ConvParams P;
     P.n_groups = n_groups;
@@ -382,8 +387,8 @@ int sml_launch_conv_fwd(const SmlRowGroup *groups, int n_groups, int variant, fl
     for (int i = 0; i < n_groups; ++i) { P.g[i] = groups[i]; if (groups[i].n > max_n) max_n = groups[i].n; }
     if (max_n == 0) return SML_OK;
     dim3 grid(grid_for_rows(max_n), n_groups);
-    if (variant == SML_VARIANT_COM) SML_CUDA_OK(sml_launch(k_conv_fwd<3>, grid, dim3(CONV_THREADS), 0, st, P, A, Apk, rowsq, zero_y));
-    else SML_CUDA_OK(sml_launch(k_conv_fwd<2>, grid, dim3(CONV_THREADS), 0, st, P, A, Apk, rowsq, zero_y));
+    if (variant == SML_VARIANT_COM) SML_CUDA_OK(sml_launch(k_conv_fwd<3>, grid, dim3(CONV_THREADS), 0, st, P, A, Apk, rowsq, zero_y, zero_dA));
+    else SML_CUDA_OK(sml_launch(k_conv_fwd<2>, grid, dim3(CONV_THREADS), 0, st, P, A, Apk, rowsq, zero_y, zero_dA));
     SML_LAUNCH_OK();
     return SML_OK;
 }

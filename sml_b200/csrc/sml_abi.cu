@@ -44,6 +44,15 @@ int sml_use_fused_fc2() {
     return v;
 }
 
+int sml_use_fused_loss() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SML_FUSE_LOSS");
+        v = (e && strcmp(e, "0") == 0) ? 0 : 1;
+    }
+    return v;
+}
+
 int sml_use_pdl() {
     static int v = -1;
     if (v < 0) {

@@ -144,8 +144,9 @@ struct SmlRowGroup {
 // conv prologue: fc1 input for every row of the groups, as plain A[N,320] (or null) and/or as a packed
 // tensor-core operand Apk (umma_pack.cuh, 128-row tiles, or null); rowsq[n] = sum x_hat^2 (or null)
 // zero_y (optional): Y[N,64] rows of the groups are cleared (split-K fc2 accumulates into them)
+// zero_dA (optional): dA[N,320] rows of the groups are cleared (split-K d1 accumulates into them)
 int sml_launch_conv_fwd(const SmlRowGroup *groups, int n_groups, int variant, float *A, uint8_t *Apk, float *rowsq,
-                        cudaStream_t st, float *zero_y = nullptr);
+                        cudaStream_t st, float *zero_y = nullptr, float *zero_dA = nullptr);
 
 // conv backward.  dA [N,320].  mode 0: scatter (dx_hat + l2*x_hat) into g_tab rows (atomic);
 // mode 1: write dx_hat to d_rows [N,64];  theta_grad != null: accumulate conv1/conv2 grads.
@@ -211,7 +212,24 @@ struct SmlPkProb {
     float *Y;             // plain fc2 output [rows][ldy], zeroed by the caller (the tiles add their partial products)
     int ldy;
 };
-int sml_launch_umma_packed(const SmlPkProb *probs, int n_probs, int epi, cudaStream_t st, int ksplit = 1);
+// SML_PK_D2 with the loss fused into its prologue (no k_loss launch in the step chain): every d2 CTA computes the dY tile it
+// multiplies straight from Y (row dots, BCE / BPR derivative: the arithmetic of k_loss, conv.cu) and writes it into shared
+// memory as its packed A operand; the CTAs of output-column tile 0 also emit what k_loss emitted (plain dY, scores, the scalar
+// loss through partials + ticket in a fixed order, the fc2 bias gradients).  Rows as in sml_launch_loss.
+struct SmlPkLoss {
+    const float *Y;        // [rows][64] fc2 output
+    const float *rowsq;    // [rows] sum x_hat^2 (MF step l2 term) or null
+    int64_t B, row_pos, row_neg;
+    int loss_kind, normalize_user;
+    float l2, adaptive;
+    float *dY;             // plain dL/dY [rows][64] (transfer step: operand of the fc2 weight gradient) or null
+    float *scores;         // [2B] or null
+    float *loss_out;       // [2]
+    float *partials;       // [4 * user tiles]
+    unsigned int *ticket;
+    float *gb_user, *gb_item;   // += column sums of dY (fc2 bias gradients) or null
+};
+int sml_launch_umma_packed(const SmlPkProb *probs, int n_probs, int epi, cudaStream_t st, int ksplit = 1, const SmlPkLoss *loss = nullptr);
 // packed weight operands of the nets: per net SML_PK_THETA_BYTES
 constexpr size_t SML_PK_OFF_P1 = 0;            // W1   as B[512][320], 128-row blocks (fc1 forward)
 constexpr size_t SML_PK_OFF_P2 = 1474560;      // W2   as B[64][512],   64-row blocks (fc2 forward)
@@ -234,3 +252,5 @@ int sml_launch_transfer_fused(const float *x_t, const float *x_hat, const int64_
 int sml_use_fused_fwd();
 // 1 = the step forward fuses fc2 into the fc1 tiles (default); SML_FUSE_FC2=0 or sml_debug_set_mask(4096) keep two launches
 int sml_use_fused_fc2();
+// 1 = the step computes loss + dL/dY inside the d2 GEMM (default); SML_FUSE_LOSS=0 or sml_debug_set_mask(8192) keep k_loss
+int sml_use_fused_loss();

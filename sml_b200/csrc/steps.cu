@@ -174,8 +174,10 @@ int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, b
     // step: 70.8 -> 68.0 us; at 3 072 rows the 128 x 128 fc1 tiles + a separate fc2 are faster: 84.6 vs 92.1 us)
     const bool fuse_fc2 = tc && sml_use_fused_fc2() && (r.user_tiles + r.item_tiles) <= 12 && !(sml_debug_mask() & (128 | 4096));
     const bool zero_y = tc && (fuse_fc2 || step_ksplit(r, 0) > 1), zero_dA = tc && step_ksplit(r, 1) > 1;
+    // loss + dL/dY inside the d2 GEMM (umma_packed.cu, SmlPkLoss): no k_loss launch in the chain (MF step at B = 1024: 84.2 -> 78.2 us; the transfer step stays at 66.7 us, its tail is bound by the two gradient branches)
+    const bool fuse_loss = tc && sml_use_fused_loss() && !(sml_debug_mask() & (4 | 8192));
     rc = sml_launch_conv_fwd(g, 3, a->variant, (!tc || need_plain_A) ? w.A : nullptr, tc ? w.Apk : nullptr,
-                             want_rowsq ? w.rowsq : nullptr, st, zero_y ? w.Y : nullptr);
+                             want_rowsq ? w.rowsq : nullptr, st, zero_y ? w.Y : nullptr, (zero_dA && fuse_loss) ? w.dA : nullptr);
     if (rc) return rc;
     if (ss) SML_CUDA_OK(cudaStreamWaitEvent(st, ss->join2, 0));
     if (sml_debug_mask() & 256) return SML_OK;
@@ -216,9 +218,11 @@ int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, b
     }
     const int dbg = sml_debug_mask();
     if (dbg & 8) return SML_OK;
-    rc = sml_launch_loss(w.Y, want_rowsq ? w.rowsq : nullptr, B, r.Bp, r.Bp + B, a->loss, a->variant == SML_VARIANT_CONV, l2, w.dY,
-                         tc ? w.dYpk : nullptr, scores, a->loss_out, w.partials, w.ticket, st, gbu2, gbi2, zero_dA ? w.dA : nullptr, adaptive);
-    if (rc) return rc;
+    if (!fuse_loss) {
+        rc = sml_launch_loss(w.Y, want_rowsq ? w.rowsq : nullptr, B, r.Bp, r.Bp + B, a->loss, a->variant == SML_VARIANT_CONV, l2, w.dY,
+                             tc ? w.dYpk : nullptr, scores, a->loss_out, w.partials, w.ticket, st, gbu2, gbi2, zero_dA ? w.dA : nullptr, adaptive);
+        if (rc) return rc;
+    }
     if (dbg & 4) return SML_OK;
     // dZ1 = (dY W2) * GELU'(Z1)
     if (tc) {
@@ -226,6 +230,12 @@ int forward_and_loss(const sml_step_args *a, const StepWs &w, bool want_rowsq, b
         // plain dZ1 is only read by the weight gradients (transfer step); the MF step keeps just the packed copy
         pk_pair(p, r, w.dYpk, 2, SML_PK_OFF_P3, 512, a->theta, 0, w.Z1, need_plain_A ? w.dZ1 : nullptr, 512, w.dZpk, w.theta_pk);
         if (g_theta) { p[0].colsum = g_theta + SML_OFF_F1B; p[1].colsum = g_theta + SML_NET_STRIDE + SML_OFF_F1B; }
+        if (fuse_loss) {
+            // plain dY is only read by the fc2 weight gradient (g_theta != null)
+            SmlPkLoss L = {w.Y, want_rowsq ? w.rowsq : nullptr, B, r.Bp, r.Bp + B, a->loss, a->variant == SML_VARIANT_CONV ? 1 : 0, l2, adaptive,
+                           g_theta ? w.dY : nullptr, scores, a->loss_out, w.partials, w.ticket, gbu2, gbi2};
+            return sml_launch_umma_packed(p, 2, SML_PK_D2, st, 1, &L);
+        }
         return sml_launch_umma_packed(p, 2, SML_PK_D2, st);
     }
     SmlGemmProb d2[2] = {

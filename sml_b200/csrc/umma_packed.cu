@@ -16,6 +16,8 @@
 //   warps 2-9          epilogue: tcgen05.ld (one accumulator row per thread) -> fused bias / GELU / GELU'
 //                      -> 128-byte-contiguous packed stores for the next GEMM (+ plain row stores)
 #include "sml_common.cuh"
+#include <string.h>
+
 #include "umma_pack.cuh"
 
 namespace {
@@ -30,7 +32,7 @@ constexpr int PKG_MAX_PROBS = 4;
 // epilogue sums with round-to-nearest adds, which brings the GEMMs back to FFMA-class accuracy.
 constexpr int PKG_NACC = 4;
 
-struct PkParams { SmlPkProb p[PKG_MAX_PROBS]; int ksplit; };
+struct PkParams { SmlPkProb p[PKG_MAX_PROBS]; int ksplit; SmlPkLoss L; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -96,8 +98,26 @@ template <int BN, bool FUSE = false> struct PkSmem {
     static constexpr uint32_t A_BYTES = pk_block_bytes(128), B_BYTES = pk_block_bytes(BN);
     static constexpr uint32_t STAGE = A_BYTES + B_BYTES;
     static constexpr uint32_t W2_BYTES = FUSE ? 2 * pk_block_bytes(64) : 0;      // fused fc2: this CTA's 64-wide K slice of W2 (2 chunks)
-    static constexpr uint32_t TOTAL = PKG_STAGES * STAGE + W2_BYTES + 128;
+    static constexpr uint32_t RED_BYTES = 384;                                    // fused loss: block reduction scratch
+    static constexpr uint32_t TOTAL = PKG_STAGES * STAGE + W2_BYTES + RED_BYTES + 128;
 };
+
+// loss terms of one triple from its two scores (the arithmetic of k_loss, conv.cu; model/conv_transfer.py:120-134)
+__device__ __forceinline__ void pk_loss_terms(int loss_kind, float sp, float sn, float invB, float &dsp, float &dsn, float &lpos, float &lneg) {
+    if (loss_kind == SML_LOSS_BCE) {
+        const float gp = sml_sigmoid(sp), gn = sml_sigmoid(sn);
+        const float ap = gp + 1e-15f, an = (1.0f - gn) + 1e-15f;     // conv_transfer.py:124-125
+        lpos = logf(ap); lneg = logf(an);
+        dsp = -(gp * (1.0f - gp)) / ap * invB;
+        dsn = (gn * (1.0f - gn)) / an * invB;
+    } else {
+        const float x = sp - sn;                                      // :128
+        lpos = fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x)));              // -logsigmoid(x) = softplus(-x)
+        lneg = 0.f;
+        dsp = -sml_sigmoid(-x);
+        dsn = -dsp;
+    }
+}
 
 // BROWS = rows per block of the packed B operand in memory.  BROWS == BN: one bulk copy per block.  BROWS = 128 with BN = 64
 // (small batches: twice the CTAs, each pulling less through its SM's L2 port and running half the epilogue): the 64 rows
@@ -105,11 +125,14 @@ template <int BN, bool FUSE = false> struct PkSmem {
 // FUSE (fc1 only, BN = 64): the CTA goes on to multiply its 128 x 64 tile of GELU(Z1) -- kept in shared memory as the next
 // A operand instead of being written to HBM in packed form -- with the matching 64-wide K slice of W2 and adds the partial
 // Y[128 x 64] into the (pre-zeroed) fc2 output with fp32 atomics: fc1 and fc2 in one launch, an 8-way split-K fc2.
-template <int BN, int EPI, int BROWS = BN, bool FUSE = false>
+// LOSS (d2 only): the A operand (dY, K = 64: two chunks) is not read from memory but computed by the epilogue warps from Y before
+// the main loop -- loss + dL/dY fused into the GEMM that consumes them (SmlPkLoss, sml_common.cuh).
+template <int BN, int EPI, int BROWS = BN, bool FUSE = false, bool LOSS = false>
 __global__ void __launch_bounds__(PKG_THREADS, 1)
 k_umma_packed(PkParams P) {
     static_assert(BROWS == BN || (BROWS == 128 && BN == 64), "unsupported packed-B block shape");
     static_assert(!FUSE || (EPI == SML_PK_FC1 && BN == 64), "fc2 can only be fused into the 128 x 64 fc1 tiles");
+    static_assert(!LOSS || (EPI == SML_PK_D2 && !FUSE), "the loss can only be fused into the d2 GEMM");
     extern __shared__ __align__(128) uint8_t smem[];
     using S = PkSmem<BN, FUSE>;
     // split-K: blockIdx.z = problem * ksplit + slice.  A single CTA streaming K = 512 pulls 0.6 MB through one SM's
@@ -127,6 +150,8 @@ k_umma_packed(PkParams P) {
     uint64_t *empty = full + PKG_STAGES;
     uint64_t *done = empty + PKG_STAGES;
     uint64_t *w2_full = done + 1, *g_full = done + 2, *y_done = done + 3;          // fused fc2 only
+    uint64_t *a_full = done + 2;                                                   // fused loss only: the dY operand is in shared memory
+    float *s_red = reinterpret_cast<float *>(smem + PKG_STAGES * S::STAGE + S::W2_BYTES);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + S::TOTAL - 8);
     uint8_t *w2s = smem + PKG_STAGES * S::STAGE;                                    // W2 slice (fused fc2)
     constexpr int TMEM_COLS = FUSE ? 512 : BN * PKG_NACC;                           // + 64 columns for the partial Y
@@ -136,6 +161,7 @@ k_umma_packed(PkParams P) {
         for (int i = 0; i < PKG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(done, 1);
         if (FUSE) { mbar_init(w2_full, 1); mbar_init(g_full, PKG_EPI_THREADS); mbar_init(y_done, 1); }
+        if (LOSS) mbar_init(a_full, PKG_EPI_THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -163,8 +189,8 @@ k_umma_packed(PkParams P) {
                 const int i = c - c_beg, s = i % PKG_STAGES;
                 if (i >= PKG_STAGES) mbar_wait(&empty[s], ((i / PKG_STAGES) - 1) & 1);
                 uint8_t *st = smem + s * S::STAGE;
-                mbar_expect_tx(&full[s], S::STAGE);
-                bulk_g2s(st, a + (size_t)c * S::A_BYTES, S::A_BYTES, &full[s]);
+                mbar_expect_tx(&full[s], LOSS ? S::B_BYTES : S::STAGE);
+                if (!LOSS) bulk_g2s(st, a + (size_t)c * S::A_BYTES, S::A_BYTES, &full[s]);
                 if (BROWS == BN) {
                     bulk_g2s(st + S::A_BYTES, b + (size_t)c * B_SRC, S::B_BYTES, &full[s]);
                 } else {
@@ -180,6 +206,7 @@ k_umma_packed(PkParams P) {
         constexpr uint32_t DHI = (PK_SBO >> 4) | (1u << 14), KSTEP = (2 * PK_LBO) >> 4;
         uint32_t leader;
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+        if (LOSS) mbar_wait(a_full, 0);                                            // both dY chunks written by the epilogue warps
         for (int c = 0; c < c_end - c_beg; ++c) {
             const int s = c % PKG_STAGES;
             mbar_wait(&full[s], (c / PKG_STAGES) & 1);
@@ -228,6 +255,147 @@ k_umma_packed(PkParams P) {
         }
     } else {
         // ===== epilogue warps: straight from TMEM registers, one accumulator row per thread =====
+        if (LOSS) {
+            // ===== loss + dL/dY for the 128 rows of this tile, written as the packed A operand (two 32-column K chunks of dY) =====
+            // Eight lanes per row (lane sub = lane & 7 owns columns 8 sub .. 8 sub + 7: every row is read as one coalesced 256 B
+            // line), four rows per warp instruction, 16 rows per warp; all loads of a warp are issued before the first use, so the
+            // prologue costs one L2 round trip plus ~4 x 150 instructions of sigmoid / log arithmetic per warp.
+            const SmlPkLoss &L = P.L;
+            const int lw = warp - 2, lg = lane >> 3, sub = lane & 7;
+            const bool item_net = p.row0 >= L.row_pos;                  // row_pos = padded user rows > 0
+            const bool lead = tile_n == 0;                              // this tile's CTA that emits what k_loss emitted
+            const float invB = 1.0f / (float)L.B;
+            float gb[8];                                                // fc2 bias gradient: column sums of dY (this lane's 8 columns)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) gb[i] = 0.f;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;               // loss sums (sub == 0 lanes, user tiles)
+            float4 u4[4][2], i4[4][2], j4[4][2];
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int qrow = tile_m * 128 + lw * 16 + it * 4 + lg;  // row inside this net's rows
+                const int kind = item_net ? (qrow < L.B ? 1 : 2) : 0;   // 0 user, 1 positive, 2 negative
+                const int64_t b = qrow < p.M ? ((kind == 2) ? qrow - L.B : qrow) : 0;
+                const float4 *yu = reinterpret_cast<const float4 *>(L.Y + b * SML_D) + 2 * sub;
+                const float4 *yi = reinterpret_cast<const float4 *>(L.Y + (L.row_pos + b) * SML_D) + 2 * sub;
+                const float4 *yj = reinterpret_cast<const float4 *>(L.Y + (L.row_neg + b) * SML_D) + 2 * sub;
+                u4[it][0] = __ldcg(yu); u4[it][1] = __ldcg(yu + 1);
+                i4[it][0] = __ldcg(yi); i4[it][1] = __ldcg(yi + 1);
+                j4[it][0] = __ldcg(yj); j4[it][1] = __ldcg(yj + 1);
+            }
+            auto sum8 = [](float v) {                                   // over the 8 lanes of a row
+                v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+                return v;
+            };
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int lr = lw * 16 + it * 4 + lg;
+                const int qrow = tile_m * 128 + lr;
+                const bool ok = qrow < p.M;
+                const int kind = item_net ? (qrow < L.B ? 1 : 2) : 0;
+                const int64_t b = (kind == 2) ? qrow - L.B : qrow;
+                float u[8] = {u4[it][0].x, u4[it][0].y, u4[it][0].z, u4[it][0].w, u4[it][1].x, u4[it][1].y, u4[it][1].z, u4[it][1].w};
+                const float vi[8] = {i4[it][0].x, i4[it][0].y, i4[it][0].z, i4[it][0].w, i4[it][1].x, i4[it][1].y, i4[it][1].z, i4[it][1].w};
+                const float vj[8] = {j4[it][0].x, j4[it][0].y, j4[it][0].z, j4[it][0].w, j4[it][1].x, j4[it][1].y, j4[it][1].z, j4[it][1].w};
+                float inv_n = 1.0f;
+                if (L.normalize_user) {   // ConvTransfer 'user': x / ||x||.detach()  (conv_transfer.py:62-63)
+                    float q = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) q = fmaf(u[i], u[i], q);
+                    const float nrm = sqrtf(sum8(q));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) u[i] = u[i] / nrm;
+                    inv_n = 1.0f / nrm;
+                }
+                float sp = 0.f, sn = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { sp = fmaf(u[i], vi[i], sp); sn = fmaf(u[i], vj[i], sn); }
+                sp = sum8(sp); sn = sum8(sn);
+                float dsp, dsn, lpos, lneg;
+                pk_loss_terms(L.loss_kind, sp, sn, invB, dsp, dsn, lpos, lneg);
+                float d[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float du = (dsp * vi[i] + dsn * vj[i]) * inv_n;
+                    d[i] = !ok ? 0.f : (kind == 0 ? du : (kind == 1 ? dsp : dsn) * u[i]);
+                }
+                // columns 8 sub .. 8 sub + 7 = K chunk sub / 4, quads 2 (sub % 4) and 2 (sub % 4) + 1
+                uint8_t *blk = smem + (size_t)(sub >> 2) * S::STAGE + (uint32_t)(lr >> 3) * PK_SBO + (uint32_t)(2 * (sub & 3)) * PK_LBO + (uint32_t)(lr & 7) * 16;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    float h[4], l[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) pk_split(d[4 * q + i], h[i], l[i]);
+                    *reinterpret_cast<float4 *>(blk + q * PK_LBO) = make_float4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<float4 *>(blk + q * PK_LBO + pk_half_bytes(128)) = make_float4(l[0], l[1], l[2], l[3]);
+                }
+                if (lead && ok) {
+                    if (L.dY) {
+                        float4 *dst = reinterpret_cast<float4 *>(L.dY + (p.row0 + qrow) * SML_D) + 2 * sub;
+                        dst[0] = make_float4(d[0], d[1], d[2], d[3]); dst[1] = make_float4(d[4], d[5], d[6], d[7]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) gb[i] += d[i];
+                    if (kind == 0 && sub == 0) {
+                        a0 += lpos; a1 += lneg;
+                        if (L.rowsq) {
+                            a2 += __ldcg(L.rowsq + b) + __ldcg(L.rowsq + L.row_pos + b) + __ldcg(L.rowsq + L.row_neg + b);
+                            if (L.adaptive != 0.f) a3 += sqrtf(__ldcg(L.rowsq + b));       // transfer.py:490-499
+                        }
+                        if (L.scores) { L.scores[b] = sp; L.scores[L.B + b] = sn; }
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(a_full)) : "memory");
+            if (lead) {
+                // s_red: [0, 32) loss sums of the 8 warps, [32, 96) the 64 column sums of dY
+                a0 += __shfl_xor_sync(0xffffffffu, a0, 8); a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, 8); a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+                a2 += __shfl_xor_sync(0xffffffffu, a2, 8); a2 += __shfl_xor_sync(0xffffffffu, a2, 16);
+                a3 += __shfl_xor_sync(0xffffffffu, a3, 8); a3 += __shfl_xor_sync(0xffffffffu, a3, 16);
+                if (lane == 0) { s_red[4 * lw] = a0; s_red[4 * lw + 1] = a1; s_red[4 * lw + 2] = a2; s_red[4 * lw + 3] = a3; }
+                if (L.gb_user && lw == 0) { s_red[32 + lane] = 0.f; s_red[64 + lane] = 0.f; }
+                asm volatile("bar.sync 1, %0;" ::"n"(PKG_EPI_THREADS) : "memory");
+                if (L.gb_user) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        gb[i] += __shfl_xor_sync(0xffffffffu, gb[i], 8); gb[i] += __shfl_xor_sync(0xffffffffu, gb[i], 16);
+                    }
+                    if (lane < 8) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) atomicAdd(&s_red[32 + 8 * sub + i], gb[i]);
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(PKG_EPI_THREADS) : "memory");
+                    if (lw < 2) atomicAdd((item_net ? L.gb_item : L.gb_user) + 32 * lw + lane, s_red[32 + 32 * lw + lane]);
+                }
+                if (!item_net && lw == 0 && lane == 0) {
+                    // scalar loss: fixed-order sums (warp -> CTA -> partials[] -> the last user tile to arrive), like k_loss
+                    float t4[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int ww = 0; ww < 8; ++ww) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) t4[k] += s_red[4 * ww + k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) L.partials[4 * tile_m + k] = t4[k];
+                    __threadfence();
+                    const unsigned n_user_tiles = (unsigned)P.p[0].m_tiles;
+                    if (atomicAdd(L.ticket, 1u) == n_user_tiles - 1) {
+                        __threadfence();
+                        float ps = 0.f, ns = 0.f, qs = 0.f, ad = 0.f;
+                        for (unsigned i = 0; i < n_user_tiles; ++i) {
+                            ps += __ldcg(L.partials + 4 * i); ns += __ldcg(L.partials + 4 * i + 1);
+                            qs += __ldcg(L.partials + 4 * i + 2); ad += __ldcg(L.partials + 4 * i + 3);
+                        }
+                        float loss = (L.loss_kind == SML_LOSS_BCE) ? (-(ps * invB)) + (-(ns * invB)) : ps;   // -mean - mean | -sum(logsigmoid)
+                        loss = loss + L.l2 * (0.5f * qs);                          // transfer.py:486-488
+                        if (L.adaptive != 0.f) loss = loss + L.adaptive * ad;       // :490-499
+                        L.loss_out[0] = loss;
+                        L.loss_out[1] += loss;
+                        *L.ticket = 0;                                              // re-arm for the next launch (graph replay)
+                    }
+                }
+            }
+        }
         mbar_wait(done, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int ew = warp - 2;                               // 0..7
@@ -384,9 +552,9 @@ __global__ void __launch_bounds__(256) k_pack_theta(const float *__restrict__ th
     }
 }
 
-template <int BN, int EPI, int BROWS = BN, bool FUSE = false>
+template <int BN, int EPI, int BROWS = BN, bool FUSE = false, bool LOSS = false>
 int launch_pk(const PkParams &P, dim3 grid, cudaStream_t st) {
-    auto kern = k_umma_packed<BN, EPI, BROWS, FUSE>;
+    auto kern = k_umma_packed<BN, EPI, BROWS, FUSE, LOSS>;
     static bool attr_set = false;
     if (!attr_set) {
         SML_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PkSmem<BN, FUSE>::TOTAL));
@@ -399,12 +567,15 @@ int launch_pk(const PkParams &P, dim3 grid, cudaStream_t st) {
 
 }  // namespace
 
-int sml_launch_umma_packed(const SmlPkProb *probs, int n_probs, int epi, cudaStream_t st, int ksplit) {
+int sml_launch_umma_packed(const SmlPkProb *probs, int n_probs, int epi, cudaStream_t st, int ksplit, const SmlPkLoss *loss) {
     SML_REQUIRE(n_probs >= 1 && n_probs <= PKG_MAX_PROBS, SML_E_BADARG, "packed gemm: bad problem count %d", n_probs);
     SML_REQUIRE(ksplit >= 1 && (ksplit == 1 || epi == SML_PK_FC2 || epi == SML_PK_D1), SML_E_BADARG,
                 "packed gemm: split-K only for the plain-output epilogues (fc2, d1)");
+    SML_REQUIRE(!loss || (epi == SML_PK_D2 && n_probs == 2 && probs[0].KC == 2 && probs[0].row0 == 0 && loss->row_pos > 0), SML_E_BADARG,
+                "packed gemm: the fused loss needs the d2 GEMM over the user net (first) and the item net");
     PkParams P;
     P.ksplit = ksplit;
+    if (loss) P.L = *loss; else memset(&P.L, 0, sizeof(P.L));
     int max_mt = 0;
     const int N = probs[0].N;
     for (int i = 0; i < n_probs; ++i) {
@@ -431,6 +602,10 @@ int sml_launch_umma_packed(const SmlPkProb *probs, int n_probs, int epi, cudaStr
         case SML_PK_FC2: SML_REQUIRE(N % 64 == 0, SML_E_BADARG, "packed gemm: fc2 N"); return launch_pk<64, SML_PK_FC2>(P, dim3(N / 64, max_mt, n_probs * ksplit), st);
         case SML_PK_D2:
             SML_REQUIRE(N % 128 == 0, SML_E_BADARG, "packed gemm: d2 N");
+            if (loss) {
+                if (narrow) return launch_pk<64, SML_PK_D2, 128, false, true>(P, dim3(N / 64, max_mt, n_probs), st);
+                return launch_pk<128, SML_PK_D2, 128, false, true>(P, dim3(N / 128, max_mt, n_probs), st);
+            }
             if (narrow) return launch_pk<64, SML_PK_D2, 128>(P, dim3(N / 64, max_mt, n_probs), st);
             return launch_pk<128, SML_PK_D2>(P, dim3(N / 128, max_mt, n_probs), st);
         case SML_PK_D1: SML_REQUIRE(N % 64 == 0, SML_E_BADARG, "packed gemm: d1 N"); return launch_pk<64, SML_PK_D1>(P, dim3(N / 64, max_mt, n_probs * ksplit), st);
