@@ -363,21 +363,32 @@ def sharded_leg(world, rank, dev, cfg=SHARDED):
         sh.mf_epoch(*tri(), Bl); sh.flush(); sh.save_hat(); sh.tr_epoch(*tri(), Bl)          # warm-up (kernel setup, NCCL channels)
         comm = CommTimers()
         sh.ex.comm = comm
+
+        def best_of(fn, reps=2):
+            """min over ``reps`` back-to-back runs (the first epoch after the replica phase of a full bench run has been seen
+            5x slow once: allocator / NCCL warm-up), with the collective timers of the fastest one."""
+            best, best_c = None, {}
+            for _ in range(reps):
+                comm.events.clear(); comm.bytes.clear()
+                ms = timed(fn)
+                c = comm.summary()
+                if best is None or ms < best:
+                    best, best_c = ms, c
+            comm.events.clear(); comm.bytes.clear()
+            return best, best_c
         a = tri()
-        ms = timed(lambda: (sh.mf_epoch(*a, Bl), sh.flush()))
+        ms, c_mf = best_of(lambda: (sh.mf_epoch(*a, Bl), sh.flush()))
         out["mf_step_ms"] = ms / S; out["mf_triples_per_s"] = Bl * w * S / ms * 1e3
-        c_mf = comm.summary(); comm.events.clear(); comm.bytes.clear()
         sh.save_hat()
-        out["updata_ms"] = timed(sh.updata)
+        out["updata_ms"], _ = best_of(sh.updata)
         out["updata_rows_per_s"] = (Ul + Il) * w / out["updata_ms"] * 1e3
         out["updata_tflops_fp32_equiv"] = (Ul + Il) * w * TRANSFER_FLOP_PER_ROW / out["updata_ms"] / 1e9
         a = tri()
-        ms = timed(lambda: sh.tr_epoch(*a, Bl))
+        ms, c_tr = best_of(lambda: sh.tr_epoch(*a, Bl))
         out["tr_step_ms"] = ms / S; out["tr_triples_per_s"] = Bl * w * S / ms * 1e3
-        c_tr = comm.summary(); comm.events.clear(); comm.bytes.clear()
         pairs = torch.stack([rnd(NP, Ul * w), rnd(NP, Il * w)], 1)
         sh.eval_fullcat(pairs, 20)
-        ms = timed(lambda: sh.eval_fullcat(pairs, 20))
+        ms, _ = best_of(lambda: sh.eval_fullcat(pairs, 20))
         out["fullcat_ms"] = ms; out["fullcat_pairs_per_s"] = NP * w / ms * 1e3
         out["fullcat_tflops_fp32_equiv"] = 2.0 * 64 * NP * w * Il * w / (ms * 1e-3) / 1e12
         per_step = lambda c: {t: dict(ms_per_step=mx(v["ms"] / S), bytes_to_peers_per_step=v["bytes_to_peers"] // S, calls_per_epoch=v["calls"])
@@ -391,7 +402,7 @@ def sharded_leg(world, rank, dev, cfg=SHARDED):
     base = run(1, 0, None)                       # the same code at world = 1 on this GPU's shard shape
     res = dict(config="configs[3]+[4]: row-sharded SML on synthetic tables, id % world ownership", world=world,
                users_per_gpu=Ul, items_per_gpu=Il, total_users=Ul * world, total_items=Il * world, batch_per_gpu=Bl,
-               steps_per_epoch=S, eval_pairs_per_gpu=NP, time="CUDA events, max over ranks; exchange planning (ids all-to-all, one host "
+               steps_per_epoch=S, eval_pairs_per_gpu=NP, time="CUDA events, max over ranks, best of 2 runs; exchange planning (ids all-to-all, one host "
                "sync per epoch) inside the timed region", world1_same_shape=base)
     if world > 1:
         res.update(run(world, rank, None))

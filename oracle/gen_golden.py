@@ -317,6 +317,119 @@ def gen_select_neg(ns):
         **{"file%d" % k: f for k, f in enumerate(files)}, **tests)
 
 
+def gen_baseline(ns):
+    """The MF baselines of model/baseline.py on a tiny stream: Reservious, fine-tune and full-retrain runs
+    (SPMF.run -> run_one_stage2), base_train, compute_R_W_P and sample_batch -- with every batch the reference's
+    DataLoaders produced.  Extra shims for this module only: ``np.long`` (removed from numpy 1.24; :73,117,566),
+    ``DataLoader(num_workers=4)`` -> 0 (deterministic global-RNG consumption, like --numworkers 0 on the SML path) and a
+    no-op ``torch.save`` for base_train's hard-coded checkpoint path (:213,219).  The SPMF method itself cannot run in the
+    reference (run_one_stage unpacks four values into two, :250)."""
+    import contextlib
+    import importlib
+    import io
+    import re
+    import types
+    if not hasattr(np, "long"):
+        np.long = np.int64
+    bl = importlib.import_module("model.baseline")
+    U, I, NP, N, NNEG = 120, 150, 6, 96, 40
+    periods = synth.make_stream(U, I, N, NP, n_neg=NNEG, seed=31)
+    tmp = tempfile.mkdtemp(prefix="sml_golden_bl_")
+    root = synth.write_stream(tmp + "/", "mini", periods, U, I) + "/"
+    rng = np.random.default_rng(5)
+    new_user = np.sort(rng.choice(U, 25, replace=False)).astype(np.int64); new_item = np.sort(rng.choice(I, 30, replace=False)).astype(np.int64)
+    np.save(root + "test_new_user.npy", new_user); np.save(root + "test_new_item.npy", new_item)
+    out = dict(U=np.int64(U), I=np.int64(I), n_periods=np.int64(NP), new_user=new_user, new_item=new_item)
+    for p, (tr, te) in enumerate(periods):
+        out["train%d" % p] = tr.astype(np.int32); out["test%d" % p] = te.astype(np.int32)
+
+    # ---- Reservious ----
+    np.random.seed(11)
+    r = bl.Reservious(50)
+    feed = [np.stack([rng.integers(0, U, n), rng.integers(0, I, n)], 1).astype(np.int64) for n in (20, 45, 70, 30)]
+    for k, f in enumerate(feed):
+        r.updata(f)
+        out["res_feed%d" % k] = f; out["res_pool%d" % k] = r.pool.copy(); out["res_state%d" % k] = np.array([r.t, r.pool_have])
+    r2 = bl.Reservious(30)
+    r2.init_pool(feed[2])
+    out["res_init_pool"] = r2.pool.copy(); out["res_init_state"] = np.array([r2.t, r2.pool_have])
+    out["res_after_draw"] = np.array(np.random.rand())          # the generator position after all of the above
+
+    DL = torch.utils.data.DataLoader
+
+    def dl0(*a, **k):
+        k["num_workers"] = 0
+        return DL(*a, **k)
+    log = []
+
+    # (the class calls super(offlineDataset_withsample, self) by its module-global name: patch its methods, do not rebind it)
+    cls = bl.offlineDataset_withsample
+    cls_init, cls_get = cls.__init__, cls.__getitem__
+
+    def rec_init(self, *a, **k):
+        with contextlib.redirect_stdout(io.StringIO()):
+            cls_init(self, *a, **k)
+        self._rec = []
+        log.append(self._rec)
+
+    def rec_get(self, idx):
+        t = cls_get(self, idx)
+        self._rec.append((int(idx), int(t[0]), int(t[1]), int(t[2])))
+        return t
+
+    def run(method, tag, base=False):
+        del log[:]
+        args = bl.get_parse().parse_args([])
+        args.lr = 0.01; args.l2_u = args.l2_i = 1e-3; args.epochs = 2; args.batch_size = 32; args.pool_size = 0; args.pool_init_type = 0
+        torch.manual_seed(2000); np.random.seed(2002)
+        ds = bl.StreamingData(root)
+        model = bl.SPMF(args, ds, int(ds.user_num), int(ds.item_num), args.laten_dim)
+        out[tag + "_init_user"] = model.MFbase.user_laten.weight.detach().numpy().copy()
+        out[tag + "_init_item"] = model.MFbase.item_laten.weight.detach().numpy().copy()
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            if base:
+                model.base_train(3, 3, 1e-3, 2e-3)
+                model.recall = [model.test(ds.get_next(3)[1])[0]]; model.ndcg = [model.test(ds.get_next(3)[1])[1]]
+            else:
+                model.run(2, method=method)
+        losses = [float(x) for x in re.findall(r"loss:(-?[0-9.]+)", buf.getvalue())]
+        out[tag + "_losses4"] = np.array(losses)                 # printed with 4 decimals (:203,363)
+        out[tag + "_final_user"] = model.MFbase.user_laten.weight.detach().numpy().copy()
+        out[tag + "_final_item"] = model.MFbase.item_laten.weight.detach().numpy().copy()
+        out[tag + "_recall"] = np.array(model.recall, dtype=np.float64); out[tag + "_ndcg"] = np.array(model.ndcg, dtype=np.float64)
+        out[tag + "_hit_new_user"] = np.array(model.hit_new_user, dtype=np.float64)
+        out[tag + "_hit_new_item"] = np.array(model.hit_new_item, dtype=np.float64)
+        out[tag + "_test_num"] = np.array(model.test_num, dtype=np.int64)
+        out[tag + "_n_logs"] = np.int64(len(log))
+        for n, rec in enumerate(log):
+            out["%s_log%d" % (tag, n)] = np.array(rec, dtype=np.int32).reshape(-1, 4)
+        return model, ds
+
+    cls.__init__, cls.__getitem__ = rec_init, rec_get
+    torch.utils.data.DataLoader = dl0
+    save = torch.save
+    torch.save = lambda *a, **k: None
+    try:
+        run("fine", "fine")
+        run("full", "full")
+        model, ds = run(None, "base", base=True)
+        # ---- rank-weighted sampling on the trained model (SPMF pieces that do run) ----
+        data = np.concatenate([periods[0][0], periods[1][0]]).astype(np.int64)
+        p = model.compute_R_W_P(data)
+        out["rwp_data"] = data; out["rwp_p"] = p
+        model.all_item = np.unique(data[:, 1]); model.user_hit = None
+        model.user_hit_num_in_W_R(data)
+        np.random.seed(77)
+        bu, bi, bn = model.sample_batch(data, 48, p, 1)
+        out["sb_user"] = bu; out["sb_item"] = bi; out["sb_neg"] = bn
+    finally:
+        torch.utils.data.DataLoader = DL
+        torch.save = save
+        cls.__init__, cls.__getitem__ = cls_init, cls_get
+    npz("baseline.npz", **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
@@ -326,7 +439,7 @@ def main():
     gens = dict(transfer_fwd=gen_transfer_fwd, run_mf=gen_run_mf, mf_steps=gen_mf_steps, tr_steps=gen_tr_steps,
                 eval=gen_eval, period_run=gen_period_run, period_run_stop=lambda n: gen_period_run(n, stop=True),
                 period_run_news=lambda n: gen_period_run(n, news=True), period_run_opts=lambda n: gen_period_run(n, opts=True),
-                select_neg=gen_select_neg)
+                select_neg=gen_select_neg, baseline=gen_baseline)
     for name, fn in gens.items():
         if a.only and name not in a.only.split(","):
             continue

@@ -69,21 +69,6 @@ def test_device_sampler_run(golden, tmp_path):
     assert len(m.recall) == 3 and abs(np.mean(m.recall) - np.mean(g["recall"])) < 0.15
 
 
-def test_baseline_trainers_learn():
-    """Fine-tune / full-retrain baselines on the plain-MF kernels: the loss falls and the positives move up."""
-    from sml_b200.data import synth
-    from sml_b200.model.baseline import FineTune, FullRetrain
-    periods = synth.make_stream(300, 400, 3000, 3, n_neg=50, seed=4)
-    for cls in (FineTune, FullRetrain):
-        torch.manual_seed(0)
-        t = cls(300, 400, lr=0.01, l2_u=1e-5, l2_i=1e-5, batch_size=256)
-        r0, _ = t.test(periods[1][1], topK=10)
-        first = t.run_period(periods[0][0], epochs=1)[0]
-        last = t.run_period(periods[1][0], epochs=6)[-1]
-        r1, _ = t.test(periods[1][1], topK=10)
-        assert last < first and r1 > r0 + 0.05, (cls.__name__, first, last, r0, r1)
-
-
 def test_row_lazy_adam_is_bit_identical_to_the_dense_sweep():
     """ops.adam_rows / adam_flush replay the zero-gradient steps a row missed: after a flush the table, exp_avg and
     exp_avg_sq must equal the dense sweep (model/transfer.py:392, dense torch.optim.Adam over nn.Embedding) bit for bit,
