@@ -190,6 +190,7 @@ class meta_train(object):
         self._loss = torch.zeros(2, dtype=torch.float32, device=self.device)
         self._ws = {}
         self._dev_cache = {}
+        self._free_bufs = []                       # [(int64 device buffer, event)] period-file buffers waiting for reuse
         self.dev_cache_cap = 6                     # period files kept resident on the device
         self.prefetch = os.environ.get("SML_PREFETCH", "1") != "0"   # upload the next period's files during the current one (prefetch_files)
         self._copy_stream = None
@@ -204,6 +205,15 @@ class meta_train(object):
         self._eval_cache = None
         self.eval_passes = dict(scored=0, reused=0)   # evaluations that launched the scoring kernel / reused a kept pass
         self.events = EventTimers(False)           # CUDA-event phase timers (bench.py switches them on)
+        # Nothing in a period's control flow depends on a loss or a metric value, so they are not read back one by one (60 blocking
+        # reads per period, each leaving the GPU idle while the host samples the next epoch): they stay on the device, the prints /
+        # writer calls / list appends that consume them are queued in order and run at the end of train_one_stage3 after ONE
+        # device->host copy (flush_deferred).  The host therefore runs ahead of the GPU inside a period and its sampling work hides
+        # behind the epoch graphs.  SML_DEFER=0 reads every value where the reference does (prints appear immediately).
+        self.defer = os.environ.get("SML_DEFER", "1") != "0"
+        self._pending = []                         # [(device tensor, post-processing)] values still on the device
+        self._later_q = []                         # [callable(values)] consumers, in program order
+        self._stage_depth = 0                      # > 0 inside train_one_stage3 (which flushes once, at its end)
 
         self.recall = []
         self.ndcg = []
@@ -236,17 +246,54 @@ class meta_train(object):
         if hit is not None and hit[0] is arr:
             if hit[2] is not None:                       # uploaded ahead of time on the copy stream (prefetch_files)
                 torch.cuda.current_stream().wait_event(hit[2])
-                hit[1].record_stream(torch.cuda.current_stream())     # allocated on the copy stream, used on this one
                 self._dev_cache[key] = (arr, hit[1], None)
             return hit[1]
-        t = torch.from_numpy(np.ascontiguousarray(arr)).to(self.device, dtype=torch.int64, non_blocking=False)
+        src = torch.from_numpy(np.ascontiguousarray(arr))
+        if src.dtype != torch.int64:
+            src = src.to(torch.int64)
+        t, _ = self._file_buffer(src.shape)              # (a recycled buffer was released on this same stream: already ordered)
+        t.copy_(src, non_blocking=False)
         self._cache_put(key, arr, t, None)
         return t
 
+    def _file_buffer(self, shape):
+        """Device buffer for one period file, from a pool that is never returned to the allocator: a fresh 600 MB block per
+        period costs up to 180 ms of cudaMalloc / allocator housekeeping (measured), a recycled one nothing.
+        -> (int64 view of the requested shape, event after which the buffer may be overwritten or None)."""
+        self._make_room()
+        n = 1
+        for d in shape:
+            n *= int(d)
+        pick = None
+        for i, (buf, _) in enumerate(self._free_bufs):
+            # smallest sufficient buffer, but never a 600 MB one for a 1 MB file (the next large file would allocate afresh)
+            if n <= buf.numel() <= 4 * max(n, 1) and (pick is None or buf.numel() < self._free_bufs[pick][0].numel()):
+                pick = i
+        if pick is None:
+            buf = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
+            ev = torch.cuda.Event()                      # the block may have been freed by work still queued on this stream
+            ev.record(torch.cuda.current_stream())
+        else:
+            buf, ev = self._free_bufs.pop(pick)
+        t = buf[:n].view(tuple(shape))
+        t._sml_buf = buf
+        return t, ev
+
     def _cache_put(self, key, arr, t, event):
-        while len(self._dev_cache) > self.dev_cache_cap:
-            self._dev_cache.pop(next(iter(self._dev_cache)))
+        self._make_room()
         self._dev_cache[key] = (arr, t, event)
+
+    def _make_room(self):
+        """Evict the oldest cached files (their buffers go back to the pool) -- called BEFORE a new buffer is taken."""
+        while len(self._dev_cache) > self.dev_cache_cap:
+            _, old, copied = self._dev_cache.pop(next(iter(self._dev_cache)))
+            buf = getattr(old, "_sml_buf", None)
+            if buf is not None:                          # back to the pool once everything enqueued so far has run
+                if copied is not None:                   # prefetched and never read: its upload may still be in flight
+                    torch.cuda.current_stream().wait_event(copied)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                self._free_bufs.append((buf, ev))
 
     def prefetch_files(self, arrs):
         """Start the host->device copy of period files that a LATER stage will need, on a side stream, so that the
@@ -260,8 +307,11 @@ class meta_train(object):
             src = torch.from_numpy(np.ascontiguousarray(arr))
             if src.dtype != torch.int64:
                 src = src.to(torch.int64)
+            t, free_ev = self._file_buffer(src.shape)
             with torch.cuda.stream(self._copy_stream):
-                t = src.to(self.device, non_blocking=True)
+                if free_ev is not None:
+                    self._copy_stream.wait_event(free_ev)
+                t.copy_(src, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self._copy_stream)
             self._cache_put(id(arr), arr, t, ev)
@@ -310,8 +360,68 @@ class meta_train(object):
         return u, i, j
 
     def _upload(self, arrs):
-        return [x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.int64)).to(self.device)
-                for x in arrs]
+        """Host id arrays -> device, through pinned staging buffers on the copy stream: a pageable cudaMemcpyAsync on the compute
+        stream would block the host until the GPU has drained everything enqueued before it (the host runs ahead, see ``defer``)."""
+        if all(isinstance(x, torch.Tensor) for x in arrs):
+            return list(arrs)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        out = []
+        cur = torch.cuda.current_stream()
+        for x in arrs:
+            if isinstance(x, torch.Tensor):
+                out.append(x)
+                continue
+            a = np.ascontiguousarray(x, dtype=np.int64)
+            stage = torch.empty(a.shape, dtype=torch.int64, pin_memory=True)
+            stage.numpy()[...] = a
+            with torch.cuda.stream(self._copy_stream):
+                t = stage.to(self.device, non_blocking=True)
+            t.record_stream(cur)
+            out.append(t)
+        ev = torch.cuda.Event()
+        ev.record(self._copy_stream)
+        cur.wait_event(ev)
+        return out
+
+    # ------------------------------------------------------------------ deferred reads
+    def _defer_value(self, dev_tensor, post=None):
+        """Keep a small result on the device; -> handle.  After flush_deferred ``values[handle]`` = post(host float32 tensor)."""
+        self._pending.append((dev_tensor.detach().reshape(-1).float(), post))
+        return len(self._pending) - 1
+
+    def _const_value(self, value):
+        self._pending.append((None, value))
+        return len(self._pending) - 1
+
+    def _print(self, *a):
+        """print, in order with the deferred consumers."""
+        self._later(lambda v: print(*a))
+
+    def _later(self, fn):
+        """Queue a consumer of deferred values (print, writer call, list append); runs at once when ``defer`` is off."""
+        self._later_q.append(fn)
+        if not self.defer:
+            self.flush_deferred()
+
+    def flush_deferred(self):
+        """One device->host copy of every pending value, then the queued consumers in program order."""
+        if not self._pending and not self._later_q:
+            return
+        pend, q = self._pending, self._later_q
+        self._pending, self._later_q = [], []
+        devs = [t for t, _ in pend if t is not None]
+        host = torch.cat(devs).cpu() if devs else None
+        vals, off = [], 0
+        for t, post in pend:
+            if t is None:
+                vals.append(post)
+                continue
+            h = host[off:off + t.numel()]
+            off += t.numel()
+            vals.append(post(h) if post is not None else h)
+        for fn in q:
+            fn(vals)
 
     def invalidate(self):
         """Call after writing the MF tables from OUTSIDE this class through a path torch cannot see
@@ -325,28 +435,45 @@ class meta_train(object):
         return (self._tab_version, uw.data_ptr(), iw.data_ptr(), uw._version, iw._version)
 
     def _eval(self, test_set, topK):
+        """test_model(self.MFbase, test_set, topK) -> handle of the deferred (recall, ndcg) pair (see ``defer``)."""
         t0 = time.perf_counter()
         # The reference re-scores a file even when nothing changed since its last evaluation (the "before train MF" pass
         # of outer phase p+1 repeats the last pass of phase p, model/transfer.py:445 vs :740; the three K of the real
         # test, :855-868).  A scoring pass is reused ONLY when the very same device file is evaluated again and nothing
         # has written the MF tables in between; the decision is taken afresh on every call (a hit never outlives the
-        # call that found it), and the reference's RNG draw per evaluation is still consumed inside test_model.
-        reused = False
-        if isinstance(test_set, DeviceTestSet):
-            c = self._eval_cache
-            reused = c is not None and c[0] is test_set.rows and c[1] == self._tables_key()
-            test_set._rank_cache = c[2] if reused else None
-            test_set.frozen = reused
+        # call that found it), and the reference's RNG draw per evaluation is still consumed.
+        if not isinstance(test_set, DeviceTestSet):
+            r = test_model(self.MFbase, test_set, topK=topK)
+            self.eval_passes["scored"] += 1
+            self.timers["eval"] += time.perf_counter() - t0
+            return self._const_value(r)
+        c = self._eval_cache
+        reused = c is not None and c[0] is test_set.rows and c[1] == self._tables_key()
+        test_set._rank_cache = c[2] if reused else None
+        test_set.frozen = reused
         # "eval" = evaluations that launch the scoring kernel, "eval_reused" = those that only reduce a kept rank pass
         with self.events("eval_reused" if reused else "eval"):
-            r = test_model(self.MFbase, test_set, topK=topK)
-        if isinstance(test_set, DeviceTestSet):
-            test_set.frozen = False
-            if test_set._rank_cache is not None:      # the cache holds the file tensor itself: no address aliasing
-                self._eval_cache = (test_set.rows, self._tables_key(), test_set._rank_cache)
+            # evalution/evaluation2.py:8-26 on a device-resident file: one scoring pass, per-1024-row reduction, sums
+            self.MFbase.eval()
+            if test_set.emulate_reference_rng:
+                ReferenceStream.loader_iter()          # the reference creates one DataLoader iterator per call
+            n = len(test_set)
+            if n == 0:
+                h = self._const_value((0.0, torch.tensor(0.0)))
+            else:
+                h = self._defer_value(self._score_sums(test_set, topK), lambda v, n=n: (float(v[0]) / n, (v[1] / n).clone()))
+        test_set.frozen = False
+        if test_set._rank_cache is not None:      # the cache holds the file tensor itself: no address aliasing
+            self._eval_cache = (test_set.rows, self._tables_key(), test_set._rank_cache)
         self.eval_passes["reused" if reused else "scored"] += 1
         self.timers["eval"] += time.perf_counter() - t0
-        return r
+        return h
+
+    def _score_sums(self, test_set, topK):
+        """[hits, sum of NDCG terms] of one evaluation as a device tensor (one scoring pass unless a kept one is reused)."""
+        gt, eq = test_set.ranks(self.MFbase)
+        hits, ndcg = ops.eval_reduce(gt, eq, topK, batch=test_set.batch)
+        return torch.stack([hits.sum().float(), ndcg.sum()])
 
     def get_next_data(self, stage_id):
         set_t, set_tt, now_test, val = self.dataset.next_train(stage_id)
@@ -358,15 +485,14 @@ class meta_train(object):
         self.transfer.eval()
         if val is not None:
             val = self._test_set(val)
-        print("******MF (inner) training ******")
+        self._print("******MF (inner) training ******")
         set_t_ds = self.MF_TrainDataset(set_t)
         if val is not None:
-            recall, ndcg = self._eval(val, args.topK)
-            print("before train MF test:recall:{:.4f} ndcg:{:.4f}".format(recall, ndcg))
+            h = self._eval(val, args.topK)
+            self._later(lambda v, h=h: print("before train MF test:recall:{:.4f} ndcg:{:.4f}".format(*v[h])))
             if self.need_writer:
-                self.writer.add_scalar("Acc/MF-recall" + str(args.topK), recall, self.MF_itr)
-                self.writer.add_scalar("Acc/MF-ndcg" + str(args.topK), ndcg, self.MF_itr)
-                self.writer.add_scalar("norm/user-norm", (self.MFbase.user_laten.weight.data ** 2).sum(dim=-1).mean(), self.MF_itr)
+                self._write_scalars([("Acc/MF-recall" + str(args.topK), h, 0), ("Acc/MF-ndcg" + str(args.topK), h, 1),
+                                     ("norm/user-norm", self._user_norm(), None)], self.MF_itr)
                 self.MF_itr += 1
         for epoch in range(args.MF_epochs):
             self.MFbase.train()
@@ -374,25 +500,38 @@ class meta_train(object):
             t0 = time.perf_counter()
             triples = self._triples("MF", set_t_ds, stage_id, epoch, len(set_t_ds))
             with self.events("mf_epoch"):
-                loss_all = self._mf_epoch(args, triples) / args.MF_batch_size       # :514-515
+                hl = self._mf_epoch(args, triples)                                  # loss_all / MF_batch_size (:514-515)
             self.timers["mf"] += time.perf_counter() - t0
             if val is not None:
-                recall, ndcg = self._eval(val, args.topK)
-                print("MF-stage:", stage_id, "epoch:", epoch, "loss:{:.5f}".format(loss_all), "recall:{:.4f}".format(recall),
-                      "ndcg:{:.4f}".format(ndcg))
+                h = self._eval(val, args.topK)
+                self._later(lambda v, h=h, hl=hl, epoch=epoch: print(
+                    "MF-stage:", stage_id, "epoch:", epoch, "loss:{:.5f}".format(v[hl]), "recall:{:.4f}".format(v[h][0]),
+                    "ndcg:{:.4f}".format(v[h][1])))
                 if self.need_writer:
-                    self.writer.add_scalar("Acc/MF-recall" + str(args.topK), recall, self.MF_itr)
-                    self.writer.add_scalar("Acc/MF-ndcg" + str(args.topK), ndcg, self.MF_itr)
-                    self.writer.add_scalar("Loss/MF-loss", loss_all, self.MF_itr)
+                    self._write_scalars([("Acc/MF-recall" + str(args.topK), h, 0), ("Acc/MF-ndcg" + str(args.topK), h, 1),
+                                         ("Loss/MF-loss", hl, None)], self.MF_itr)
             else:
-                print("MF-stage:", stage_id, "epoch:", epoch, "loss:", loss_all)
+                self._later(lambda v, hl=hl, epoch=epoch: print("MF-stage:", stage_id, "epoch:", epoch, "loss:", v[hl]))
             if self.need_writer:
-                self.writer.add_scalar("norm/user-norm", (self.MFbase.user_laten.weight.data ** 2).sum(dim=-1).mean(), self.MF_itr)
+                self._write_scalars([("norm/user-norm", self._user_norm(), None)], self.MF_itr)
                 self.MF_itr += 1
-            self.last_MF_loss = loss_all
+            self._later(lambda v, hl=hl: setattr(self, "last_MF_loss", v[hl]))
+        if self._stage_depth == 0:
+            self.flush_deferred()
+
+    def _user_norm(self):
+        return self._defer_value((self.MFbase.user_laten.weight.data ** 2).sum(dim=-1).mean(), lambda v: float(v[0]))
+
+    def _write_scalars(self, items, itr):
+        """writer.add_scalar(name, value, itr) for deferred values: items = [(name, handle, index into the value or None)]."""
+        def emit(v):
+            for name, h, k in items:
+                self.writer.add_scalar(name, v[h] if k is None else v[h][k], itr)
+        self._later(emit)
 
     def _mf_epoch(self, args, triples):
-        """HOT LOOP A (model/transfer.py:463-511) over one epoch of triples; returns the mean batch loss."""
+        """HOT LOOP A (model/transfer.py:463-511) over one epoch of triples; returns the handle of the deferred epoch loss
+        (mean batch loss / MF_batch_size, :514-515)."""
         user, item, neg = self._upload(triples)
         uw, iw = self.MFbase.user_laten.weight.data, self.MFbase.item_laten.weight.data
         B = int(args.MF_batch_size)
@@ -417,12 +556,12 @@ class meta_train(object):
                         (lr, args.l2, self.transfer.variant, adaptive) + tuple(t.data_ptr() for t in (
                             uw, iw, self.last_user_weight, self.last_item_weight, self.transfer.theta, ws,
                             self.MF_optimizer.adam_state, *self._mf.values(), *self._stamps.values())))
-        return self._loss[1].item() / nb
+        return self._defer_value(self._loss[1:2].clone(), lambda v, d=float(nb) * args.MF_batch_size: float(v[0]) / d)
 
     # ------------------------------------------------------------------ transfer (outer) training
     def transfer_train_onestage(self, args, set_tt, stage_id, compute_performance=False, val=None):
         """reference: model/transfer.py:644-749 (embeddings fixed, theta trained)."""
-        print("********* this is Transfer model training stage ***********")
+        self._print("********* this is Transfer model training stage ***********")
         self.MFbase.eval()
         now_test = None
         if self.TR_train_sampleTYpe == "alone":
@@ -438,11 +577,10 @@ class meta_train(object):
         else:
             raise TypeError("no such TR sample type")
         if compute_performance:
-            recall, ndcg = self._eval(now_test, args.topK)
-            print("before train transfer test:recall:{:.4f} ndcg:{:.4f}".format(recall, ndcg))
+            h = self._eval(now_test, args.topK)
+            self._later(lambda v, h=h: print("before train transfer test:recall:{:.4f} ndcg:{:.4f}".format(*v[h])))
             if self.need_writer:
-                self.writer.add_scalar("Acc/tr-TR-recall@" + str(args.topK), recall, self.TR_itr)
-                self.writer.add_scalar("Acc/tr-TR-ndcg@" + str(args.topK), ndcg, self.TR_itr)
+                self._write_scalars([("Acc/tr-TR-recall@" + str(args.topK), h, 0), ("Acc/tr-TR-ndcg@" + str(args.topK), h, 1)], self.TR_itr)
                 self.TR_itr += 1
         s_time = time.time()
         for epoch in range(args.TR_epochs):
@@ -450,23 +588,33 @@ class meta_train(object):
             t0 = time.perf_counter()
             triples = self._triples("TR", set_tt_ds, stage_id, epoch, len(set_tt_ds))
             with self.events("tr_epoch"):
-                loss_all = self._tr_epoch(args, triples)
+                hl = self._tr_epoch(args, triples)                                  # loss_all (mean batch loss)
             self.timers["tr"] += time.perf_counter() - t0
-            print("one epcohs TR time cost:", time.time() - s_time)
+            self._later(lambda v, dt=time.time() - s_time: print("one epcohs TR time cost:", dt))
             if self.need_writer:
-                self.writer.add_scalar("Loss/TR-loss", loss_all / args.TR_batch_size, self.TR_itr)
+                self._write_scalars([("Loss/TR-loss", self._scaled(hl, 1.0 / args.TR_batch_size), None)], self.TR_itr)
             if compute_performance:
                 self.updata()
-                recall, ndcg = self._eval(now_test, args.topK)
-                print("stage:{}, epcoh：{}，loss:{:.4f},*****val result  reacll:{:.4f}  ndcg:{:.4f}".format(
-                    stage_id, epoch, loss_all / args.TR_batch_size, recall, ndcg))
+                h = self._eval(now_test, args.topK)
+                self._later(lambda v, h=h, hl=hl, epoch=epoch: print("stage:{}, epcoh：{}，loss:{:.4f},*****val result  reacll:{:.4f}  ndcg:{:.4f}".format(
+                    stage_id, epoch, v[hl] / args.TR_batch_size, v[h][0], v[h][1])))
                 if self.need_writer:
-                    self.writer.add_scalar("Acc/tr-TR-recall@" + str(args.topK), recall, self.TR_itr)
-                    self.writer.add_scalar("Acc/tr-TR-ndcg@" + str(args.topK), ndcg, self.TR_itr)
+                    self._write_scalars([("Acc/tr-TR-recall@" + str(args.topK), h, 0), ("Acc/tr-TR-ndcg@" + str(args.topK), h, 1)], self.TR_itr)
             else:
-                print("stage:", stage_id, "epoch:", epoch, "transfer train loss:", loss_all / args.TR_batch_size)
-            self.last_TR_loss = loss_all
-        print("stage ", stage_id, " transfer trained finished!!!!")
+                self._later(lambda v, hl=hl, epoch=epoch: print("stage:", stage_id, "epoch:", epoch, "transfer train loss:", v[hl] / args.TR_batch_size))
+            self._later(lambda v, hl=hl: setattr(self, "last_TR_loss", v[hl]))
+        self._print("stage ", stage_id, " transfer trained finished!!!!")
+        if self._stage_depth == 0:
+            self.flush_deferred()
+
+    def _scaled(self, h, k):
+        """Handle of k * (the deferred scalar behind handle h)."""
+        self._pending.append((None, None))
+        hs = len(self._pending) - 1
+        def fill(v, h=h, hs=hs, k=k):
+            v[hs] = v[h] * k
+        self._later_q.append(fill)
+        return hs
 
     def _run_epoch(self, kind, build, triples, n, B, key_extra):
         """Enqueue one epoch: directly the first time a (kind, n, B, hyper-parameters) combination is seen, as a CUDA
@@ -501,7 +649,7 @@ class meta_train(object):
         self.graph_launches += nodes
 
     def _tr_epoch(self, args, triples):
-        """HOT LOOP B (model/transfer.py:701-728) over one epoch of triples; returns the mean batch loss."""
+        """HOT LOOP B (model/transfer.py:701-728) over one epoch of triples; returns the handle of the deferred mean batch loss."""
         user, item, neg = self._upload(triples)
         B = int(args.TR_batch_size)
         ws = self._workspace(B)
@@ -524,7 +672,7 @@ class meta_train(object):
                             self.transfer.theta, self.transfer.theta_grad, self._tr["m"], self._tr["v"], ws,
                             self.last_user_weight, self.last_item_weight, self.user_weight_hat, self.item_weight_hat,
                             self.transfer_optimizer.adam_state)))
-        return self._loss[1].item() / nb
+        return self._defer_value(self._loss[1:2].clone(), lambda v, d=float(nb): float(v[0]) / d)
 
     # ------------------------------------------------------------------ one period
     def _real_test(self, now_test_arr):
@@ -533,13 +681,26 @@ class meta_train(object):
         now_test = self._test_set(now_test_arr)       # three K on unchanged tables: _eval keeps one scoring pass
         for K, rl, nl, tag in ((20, self.recall, self.ndcg, ""), (10, self.recall_10, self.ndcg_10, " @10"),
                                (5, self.recall_5, self.ndcg_5, " @5")):
-            recall, ndcg = self._eval(now_test, K)
-            print("test result ---------{} reacll:{:.4f}  ndcg:{:.4f}".format(tag, recall, ndcg))
-            rl.append(recall)
-            nl.append(ndcg.cpu().numpy())
+            h = self._eval(now_test, K)
+
+            def consume(v, h=h, rl=rl, nl=nl, tag=tag):
+                recall, ndcg = v[h]
+                print("test result ---------{} reacll:{:.4f}  ndcg:{:.4f}".format(tag, recall, ndcg))
+                rl.append(recall)
+                nl.append(ndcg.cpu().numpy())
+            self._later(consume)
 
     def train_one_stage3(self, args, stage_id):
-        """reference: model/transfer.py:753-881 -- one period, three branches."""
+        """reference: model/transfer.py:753-881 -- one period, three branches.  Losses / metrics of the period are read back
+        once, at its end (see ``defer``): its prints come out then, in the reference's order."""
+        self._stage_depth += 1
+        try:
+            return self._train_one_stage3(args, stage_id)
+        finally:
+            self._stage_depth -= 1
+            self.flush_deferred()
+
+    def _train_one_stage3(self, args, stage_id):
         self.save_MF_weight(save_as="last")
         set_t, set_tt, now_test, val = self.get_next_data(stage_id)
         if set_t is None:
@@ -560,15 +721,15 @@ class meta_train(object):
             return True
         elif set_tt is None:                       # transfer frozen while testing (:793-825)
             s_time = time.time()
-            print("stop train transfer while test###!!!!!")
+            self._print("stop train transfer while test###!!!!!")
             args.MF_epochs = 2                     # the reference mutates args here (:796)
             self.MF_train_onestage(args, set_t, stage_id, val=val)
             self.MFbase.eval()
             self.save_MF_weight(save_as="hat")
             self.updata()
-            print("only traning time cost:", time.time() - s_time)
+            self._print("only traning time cost:", time.time() - s_time)
             self._real_test(now_test)
-            print("include test time cost:", time.time() - s_time)
+            self._print("include test time cost:", time.time() - s_time)
             return True
         else:                                      # test on D_{t+1}, then train the transfer on it (:826-881)
             for phase in range(args.multi_num):

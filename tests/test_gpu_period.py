@@ -43,9 +43,9 @@ def run_ours(g, tmp, stop, replay, news=False, opts=False):
     inner = meta._eval
 
     def logged(test_set, topK):
-        r, n = inner(test_set, topK)
-        meta.eval_log.append([float(topK), float(len(test_set)), float(r), float(n)])
-        return r, n
+        h = inner(test_set, topK)                  # handle of the deferred (recall, ndcg); read back at the end of the period
+        meta._later(lambda v, h=h, k=float(topK), n=float(len(test_set)): meta.eval_log.append([k, n, float(v[h][0]), float(v[h][1])]))
+        return h
     meta._eval = logged
     meta.run(args)
     return meta

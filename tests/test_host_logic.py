@@ -60,15 +60,15 @@ class HostProbe(meta_train):
     def _eval(self, test_set, topK):
         ReferenceStream.loader_iter()
         self.rec.append(("eval", test_set.shape[0], topK))
-        return 0.0, torch.tensor(0.0)
+        return self._const_value((0.0, torch.tensor(0.0)))
 
     def _mf_epoch(self, args, triples):
         self.rec.append(("MF", np.stack(triples, 1)))
-        return 0.0
+        return self._const_value(0.0)
 
     def _tr_epoch(self, args, triples):
         self.rec.append(("TR", np.stack(triples, 1)))
-        return 0.0
+        return self._const_value(0.0)
 
     def updata(self):
         self.rec.append(("updata",))
@@ -260,24 +260,25 @@ def test_eval_cache_never_serves_stale_ranks(monkeypatch):
 
     m = T.meta_train.__new__(T.meta_train)
     w = lambda: types.SimpleNamespace(weight=torch.nn.Parameter(torch.zeros(2, 2)))
-    m.MFbase = types.SimpleNamespace(user_laten=w(), item_laten=w())
+    m.MFbase = types.SimpleNamespace(user_laten=w(), item_laten=w(), eval=lambda: None)
     m._tab_version, m._eval_cache = 0, None
+    m.defer, m._pending, m._later_q, m._stage_depth = True, [], [], 0
     m.eval_passes = dict(scored=0, reused=0)
     m.events = EventTimers(False)
     m.timers = dict(eval=0.0)
     seen = []
 
-    def fake_test_model(model, ts, topK=10):
+    def fake_score_sums(ts, topK):
         # what DeviceTestSet.ranks does, with the table version standing in for the scores
         if not (ts.frozen and ts._rank_cache is not None):
             ts._rank_cache = ("ranks@", m._tab_version)
         seen.append(ts._rank_cache[1])
-        return 0.0, torch.tensor(0.0)
-    monkeypatch.setattr(T, "test_model", fake_test_model)
+        return torch.zeros(2)
+    m._score_sums = fake_score_sums
 
     def file_set(rows):
         ts = DeviceTestSet.__new__(DeviceTestSet)
-        ts.rows, ts.frozen, ts._rank_cache = rows, False, None
+        ts.rows, ts.frozen, ts._rank_cache, ts.emulate_reference_rng, ts.batch = rows, False, None, False, 1024
         return ts
     val_rows, test_rows = torch.zeros(3, 4, dtype=torch.int64), torch.zeros(3, 4, dtype=torch.int64)
     multi_num = 10

@@ -61,7 +61,7 @@ def main():
             finally:
                 acc[label][0] += 1; acc[label][1] += time.perf_counter() - t
         setattr(obj, name, g)
-    for n in ("_triples", "_mf_epoch", "_tr_epoch", "_eval", "updata", "save_MF_weight", "_test_set", "_sample_dataset", "prefetch_files",
+    for n in ("_triples", "_mf_epoch", "_tr_epoch", "_eval", "flush_deferred", "updata", "save_MF_weight", "_test_set", "_sample_dataset", "prefetch_files",
               "get_next_data", "_upload", "MF_TrainDataset", "_run_epoch"):
         wrap(meta, n)
     stage = 0
