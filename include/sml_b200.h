@@ -156,7 +156,12 @@ int sml_adam_dense_clipped(float *p, float *m, float *v, float *g, int64_t n, co
  *   sml_adam_rows(apply = 1): apply step t with the accumulated gradient rows g[id], re-zero them;
  *   sml_adam_flush:           bring EVERY row up to step t (before the table is read as a whole).
  * t = state[0]; state must carry the history (state[2] != 0) and no row may lag more than
- * SML_ADAM_HISTORY - 1 steps.  Duplicate ids are fine (first claimant updates the row). */
+ * SML_ADAM_HISTORY - 1 steps.  Duplicate ids are fine (first claimant updates the row).
+ * stamp[row] = SML_STAMP_IDLE marks a row whose exp_avg / exp_avg_sq have been +0 since the table was created (no gradient
+ * ever reached it): zero-gradient steps leave such a row unchanged bit for bit, so nothing is replayed and sml_adam_flush skips
+ * it on the stamp alone.  Fresh stamps for all-zero moments should be SML_STAMP_IDLE; sml_adam_flush also sets it for rows it
+ * finds with all-zero moments. */
+#define SML_STAMP_IDLE 0x7fffffff
 int sml_adam_rows(float *p, float *m, float *v, float *g, int32_t *stamp, const int64_t *ids, int64_t n_ids, int64_t n_rows,
                   const int64_t *state, int apply, double beta1, double beta2, double eps, void *stream);
 int sml_adam_flush(float *p, float *m, float *v, int32_t *stamp, int64_t n_rows, const int64_t *state, double beta1,

@@ -113,12 +113,15 @@ k_adam_rows(AdamRowsParams P, const int64_t *__restrict__ state, float b1c, floa
         int old = 0;
         if (lane == 0) old = atomicExch(G.stamp + id, target);
         old = __shfl_sync(0xffffffffu, old, 0);
-        if (old >= target) continue;
+        // SML_STAMP_IDLE: exp_avg = exp_avg_sq = +0 since the table was created -- nothing to replay, and this warp is the first
+        // to touch the row at this step
+        if (old != SML_STAMP_IDLE && old >= target) continue;
+        if (old == SML_STAMP_IDLE && !APPLY) continue;
         const size_t e = (size_t)id * SML_D + 2 * lane;
         float2 pp = *reinterpret_cast<float2 *>(G.p + e), mm = *reinterpret_cast<float2 *>(G.m + e),
                vv = *reinterpret_cast<float2 *>(G.v + e);
         // exp_avg = exp_avg_sq = +0 (a row no gradient ever reached): a zero-gradient step changes nothing, bit for bit
-        const bool idle = (__float_as_uint(mm.x) | __float_as_uint(mm.y) | __float_as_uint(vv.x) | __float_as_uint(vv.y)) == 0u;
+        const bool idle = old == SML_STAMP_IDLE || (__float_as_uint(mm.x) | __float_as_uint(mm.y) | __float_as_uint(vv.x) | __float_as_uint(vv.y)) == 0u;
         for (int s = idle ? t : old + 1; s < t; ++s) {   // the zero-gradient steps this row missed
             const float2 c = adam_hist(state, s);
             sml_adam1(pp.x, mm.x, vv.x, 0.f, b1c, beta2, b2c, c.x, c.y, eps, 0.f);
@@ -149,12 +152,21 @@ k_adam_flush(float4 *__restrict__ p, float4 *__restrict__ m, float4 *__restrict_
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4_up; i += (int64_t)gridDim.x * blockDim.x) {
         const bool live = i < n4;
         const int64_t row = i >> 4;
-        const int old = live ? stamp[row] : t;
+        const int old = live ? stamp[row] : t;           // SML_STAMP_IDLE (INT32_MAX) never needs anything
         __syncwarp();
-        if (old < t) {
-            float4 pp = p[i], mm = m[i], vv = v[i];
-            const bool idle = (__float_as_uint(mm.x) | __float_as_uint(mm.y) | __float_as_uint(mm.z) | __float_as_uint(mm.w) |
-                               __float_as_uint(vv.x) | __float_as_uint(vv.y) | __float_as_uint(vv.z) | __float_as_uint(vv.w)) == 0u;
+        const bool need = old < t;
+        float4 pp, mm, vv;
+        bool idle = true;
+        if (need) {
+            pp = p[i]; mm = m[i]; vv = v[i];
+            idle = (__float_as_uint(mm.x) | __float_as_uint(mm.y) | __float_as_uint(mm.z) | __float_as_uint(mm.w) |
+                    __float_as_uint(vv.x) | __float_as_uint(vv.y) | __float_as_uint(vv.z) | __float_as_uint(vv.w)) == 0u;
+        }
+        // a row whose moments are all +0 is marked idle: later flushes skip it on its stamp alone (4 B instead of 768 B per row --
+        // on a 27 M-row shard of which a step touches 25 k rows this is the difference between 3.7 ms and 0.1 ms per flush)
+        const unsigned idle_mask = __ballot_sync(0xffffffffu, idle);
+        const bool row_idle = ((idle_mask >> (threadIdx.x & 16)) & 0xFFFFu) == 0xFFFFu;
+        if (need) {
             for (int s = idle ? t + 1 : old + 1; s <= t; ++s) {
                 const float2 c = adam_hist(state, s);
                 sml_adam1(pp.x, mm.x, vv.x, 0.f, b1c, beta2, b2c, c.x, c.y, eps, 0.f);
@@ -163,7 +175,7 @@ k_adam_flush(float4 *__restrict__ p, float4 *__restrict__ m, float4 *__restrict_
                 sml_adam1(pp.w, mm.w, vv.w, 0.f, b1c, beta2, b2c, c.x, c.y, eps, 0.f);
             }
             if (!idle) { p[i] = pp; m[i] = mm; v[i] = vv; }
-            if ((i & 15) == 0) stamp[row] = t;
+            if ((i & 15) == 0) stamp[row] = row_idle ? SML_STAMP_IDLE : t;
         }
     }
 }

@@ -411,7 +411,8 @@ int sml_launch_conv_bwd(const SmlConvBwdGroup *groups, int n_groups, int variant
     int gx = grid_for_rows(max_n);
     // each CTA ends with 95 global atomics onto the same 95 parameters: a few dozen CTAs per group keep that cheap
     // (96 per group measured 2-6 us slower per transfer step than 32, profiles/r01_tr_step_breakdown.md)
-    if (theta) { const int cap = 32; if (gx > cap) gx = cap; }
+    // (at the 8 192-row groups of the sharded step 32 CTAs serialise 128 row halves per warp: 209 us; scale the cap with the rows)
+    if (theta) { int cap = (int)(max_n / 32); if (cap < 32) cap = 32; if (cap > 2 * sml_sm_count()) cap = 2 * sml_sm_count(); if (gx > cap) gx = cap; }
     dim3 grid(gx, n_groups);
 #define SML_CB(R_, MODE_, TH_) SML_CUDA_OK(sml_launch(k_conv_bwd<R_, MODE_, TH_>, grid, dim3(CONV_THREADS), 0, st, P, dA, l2, d_rows, adaptive))
     const bool com = variant == SML_VARIANT_COM;

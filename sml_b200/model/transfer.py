@@ -191,6 +191,7 @@ class meta_train(object):
         self._ws = {}
         self._dev_cache = {}
         self._free_bufs = []                       # [(int64 device buffer, event)] period-file buffers waiting for reuse
+        self._buf_sizes = []                       # capacities of all pooled buffers ever allocated
         self.dev_cache_cap = 6                     # period files kept resident on the device
         self.prefetch = os.environ.get("SML_PREFETCH", "1") != "0"   # upload the next period's files during the current one (prefetch_files)
         self._copy_stream = None
@@ -270,9 +271,16 @@ class meta_train(object):
             if n <= buf.numel() <= 4 * max(n, 1) and (pick is None or buf.numel() < self._free_bufs[pick][0].numel()):
                 pick = i
         if pick is None:
-            buf = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
-            ev = torch.cuda.Event()                      # the block may have been freed by work still queued on this stream
+            # first file of this size class: allocate every buffer the cache will ever hold for it now, while little or nothing
+            # is queued on the GPU (a cudaMalloc of this size has been seen to take 50-180 ms once the host runs ahead)
+            same = sum(1 for c in self._buf_sizes if n <= c <= 4 * max(n, 1))
+            want = min(8, max(1, self.dev_cache_cap + 1 - same)) if n >= (1 << 17) else 1
+            fresh = [torch.empty(max(n, 1), dtype=torch.int64, device=self.device) for _ in range(want)]
+            ev = torch.cuda.Event()                      # the blocks may have been freed by work still queued on this stream
             ev.record(torch.cuda.current_stream())
+            self._buf_sizes.extend(b.numel() for b in fresh)
+            buf = fresh.pop()
+            self._free_bufs.extend((b, ev) for b in fresh)
         else:
             buf, ev = self._free_bufs.pop(pick)
         t = buf[:n].view(tuple(shape))

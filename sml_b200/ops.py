@@ -114,8 +114,15 @@ def new_adam_state(device, history=False):
     return st
 
 
-def new_row_stamps(n_rows, state):
-    """int32 [n_rows] 'last Adam step applied' stamps, initialised to the state's current step (no sync)."""
+STAMP_IDLE = 0x7fffffff
+
+
+def new_row_stamps(n_rows, state, idle=True):
+    """int32 [n_rows] 'last Adam step applied' stamps for a table whose exp_avg / exp_avg_sq are all zero (``idle``:
+    SML_STAMP_IDLE, rows no gradient has reached yet are skipped by flushes on the stamp alone); ``idle=False``: the state's
+    current step, for moments that are already non-zero (no sync)."""
+    if idle:
+        return torch.full((n_rows,), STAMP_IDLE, dtype=torch.int32, device=state.device)
     return state[0].to(torch.int32).expand(n_rows).contiguous()
 
 

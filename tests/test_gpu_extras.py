@@ -100,7 +100,16 @@ def test_row_lazy_adam_is_bit_identical_to_the_dense_sweep():
             assert torch.equal(pl, pd)
     ops.adam_flush(pl, ml, vl, stamp, sl)
     assert torch.equal(pl, pd) and torch.equal(ml, md) and torch.equal(vl, vd)
-    assert int(stamp.min()) == T and int(stamp.max()) == T
+    # every row is at step T, except the rows no gradient ever reached: they keep SML_STAMP_IDLE (exp_avg = exp_avg_sq = 0, skipped
+    # by flushes on the stamp alone), and those are exactly the rows whose moments are all zero
+    idle = stamp == ops.STAMP_IDLE
+    assert bool(((stamp == T) | idle).all()) and 0 < int(idle.sum()) < N
+    assert torch.equal(idle, (ml == 0).all(1) & (vl == 0).all(1))
+    # stamps that start at the current step (moments not known to be zero) end the same way: the flush marks the idle rows itself
+    st2 = ops.new_row_stamps(N, sl, idle=False)
+    ops.adam_tick(sl, 0.01)
+    ops.adam_flush(pl, ml, vl, st2, sl)
+    assert torch.equal(st2 == ops.STAMP_IDLE, idle) and bool(((st2 == T + 1) | (st2 == ops.STAMP_IDLE)).all())
 
 
 def test_mf_epoch_row_lazy_adam_matches_dense():
