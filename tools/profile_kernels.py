@@ -31,11 +31,16 @@ def main():
     a = ops.make_step_args(user=u, item=i, neg=j, last_user=lu, last_item=li, hat_user=hu.clone(), hat_item=hi.clone(), theta=tr.theta,
                            adam_state=ops.new_adam_state(dev), lr=1e-4, l2=1e-6, loss_out=loss,
                            g_user=z(hu), g_item=z(hi), m_user=z(hu), v_user=z(hu), m_item=z(hi), v_item=z(hi))
+    Bt = 256
+    a_tr = ops.make_step_args(user=u[:Bt].contiguous(), item=i[:Bt].contiguous(), neg=j[:Bt].contiguous(), last_user=lu, last_item=li, hat_user=hu.clone(),
+                              hat_item=hi.clone(), theta=tr.theta, adam_state=ops.new_adam_state(dev), lr=1e-5, l2=1e-4, loss_out=loss,
+                              g_theta=tr.theta_grad, m_theta=z(tr.theta), v_theta=z(tr.theta))
     eu = torch.randint(0, U, (16384,), generator=g).to(dev); ep = torch.randint(0, I, (16384,), generator=g).to(dev)
     ipk = ops.pack_rows(hi)
     work = [("eval_candidates 75000x1001", lambda: ops.eval_candidates(hu, hi, rows), N * 264264 / 1e9, "GB"),
             ("transfer_forward 59082 rows", lambda: ops.transfer_forward(lu, hu, tr.theta[:ops.NET_STRIDE], out=out), U * 403456 / 1e12, "TFLOP"),
             ("mf_step B=1024", lambda: ops.mf_step(a), 1024, "triples"),
+            ("tr_step B=256", lambda: ops.tr_step(a_tr), 256, "triples"),
             ("fullcat_rank 16384 users x 122816 items", lambda: ops.fullcat_ranks(hu, hi, eu, ep, items_packed=ipk, n_items=I), 16384 * I * 128 / 1e12, "TFLOP")]
     # round 2 additions: fused transfer forward, fused plain-MF step, row-lazy Adam, owner-side exchange kernels, top-k
     big = 1_000_000
