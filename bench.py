@@ -94,7 +94,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "250"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.lines.append(line.strip())
         except Exception:
@@ -548,8 +548,11 @@ def run_ours(a):
         if world > 1:
             dist.barrier()
         meta.events.enabled = True
-        sampler = ClockSampler(local)
-        sampler.start()
+        # rank 0 samples its own GPU (it prints the line).  One nvidia-smi poller per rank was measured to stall the other ranks' work
+        # submission at 8 GPUs (NVML queries from 8 processes serialise in the driver: transfer epochs 192 -> 412 ms on rank 0)
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler is not None:
+            sampler.start()
         launches0 = lib().sml_launch_count() + meta.graph_launches
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -560,7 +563,7 @@ def run_ours(a):
         if world > 1:
             dist.barrier()
         dev_s = ev0.elapsed_time(ev1) / 1e3
-        clocks = sampler.stop()
+        clocks = sampler.stop() if sampler is not None else None
         launches = lib().sml_launch_count() + meta.graph_launches - launches0      # direct launches + kernels inside graph replays
         phases = meta.events.summary()
         meta.events.enabled = False

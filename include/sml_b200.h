@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SML_ABI_VERSION 3
+#define SML_ABI_VERSION 4
 
 #define SML_OK 0
 #define SML_E_BADARG (-1)
@@ -211,6 +211,11 @@ typedef struct {
      *   by min(1, max_norm / (||g||_2 + 1e-6)) before the Adam update (torch.nn.utils.clip_grad_norm_).  The same call in
      *   the MF step (:507-510) clips gradients that no optimizer ever applies: nothing to do there. */
     double adaptive_beta, clip_max_norm;
+    /* sml_run_mf_grads only.  0: d_rows uses the step row layout (sml_step_rows).  1: the gradient of the row gathered
+     * through id k is written to d_rows[k] (user rows) / d_rows[*row_pos + k] (positive and negative item rows, which
+     * index one [2 * batch]-row table): when the "tables" are row pairs received from an exchange and the ids are the
+     * exchange's inverse permutation, d_rows comes out in the order the gradients are sent back (sml_b200/shard.py). */
+    int32_t d_rows_by_id;
 } sml_step_args;
 
 size_t sml_step_workspace_bytes(int64_t batch);

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsml_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 D = 64
 OFF_C1W, OFF_C1B, OFF_C2W, OFF_C2B = 0, 32, 64, 128
 OFF_F1W, OFF_F1B, OFF_F2W, OFF_F2B = 160, 164000, 164512, 197280
@@ -36,6 +36,7 @@ class StepArgs(C.Structure):
         ("loss_out", _vp), ("workspace", _vp), ("workspace_bytes", _sz), ("table_pitch", _i64),
         ("stamp_user", _vp), ("stamp_item", _vp),
         ("adaptive_beta", _dbl), ("clip_max_norm", _dbl),
+        ("d_rows_by_id", _i32),
     ]
 
 

@@ -209,7 +209,7 @@ k_conv_bwd(ConvBwdParams P, const float *__restrict__ dA, float l2, float *__res
                 }
                 atomicAdd(bg.g_tab + id * SML_D + lane + 32 * h, gsc);
             } else if (d_rows) {
-                d_rows[(g.row0 + r) * SML_D + lane + 32 * h] = dx1;
+                d_rows[(bg.d_base >= 0 ? bg.d_base + id : g.row0 + r) * SML_D + lane + 32 * h] = dx1;
             }
         }
     }

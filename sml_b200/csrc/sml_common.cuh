@@ -154,6 +154,7 @@ struct SmlConvBwdGroup {
     SmlRowGroup g;
     float *g_tab;      // dense gradient table for scatter (mode 0) or null
     float *g_theta;    // this group's net gradient block or null
+    int64_t d_base;    // mode 1: >= 0 -> the row gathered through id k writes d_rows[d_base + k]; < 0 -> d_rows[row0 + r]
 };
 // adaptive (scatter mode, first group = the user rows): adds 2 * adaptive * x_hat / ||x_hat|| per occurrence (--need_adaptive)
 int sml_launch_conv_bwd(const SmlConvBwdGroup *groups, int n_groups, int variant, const float *dA, float l2,

@@ -332,7 +332,7 @@ int mf_step_impl(const sml_step_args *a, bool pack_theta, void *stream) {
         if (rc) return rc;
         SmlRowGroup g[3];
         make_groups(a, g);
-        SmlConvBwdGroup bg[3] = {{g[0], a->g_user, nullptr}, {g[1], a->g_item, nullptr}, {g[2], a->g_item, nullptr}};
+        SmlConvBwdGroup bg[3] = {{g[0], a->g_user, nullptr, -1}, {g[1], a->g_item, nullptr, -1}, {g[2], a->g_item, nullptr, -1}};
         rc = sml_launch_conv_bwd(bg, 3, a->variant, w.dA, (float)a->l2, nullptr, st, (float)a->adaptive_beta);
         if (rc) return rc;
     }
@@ -477,7 +477,7 @@ int sml_tr_step(const sml_step_args *a, void *stream) {
         SmlRowGroup g[3];
         make_groups(a, g);
         float *gu = a->g_theta, *gi = a->g_theta + SML_NET_STRIDE;
-        SmlConvBwdGroup bg[3] = {{g[0], nullptr, gu}, {g[1], nullptr, gi}, {g[2], nullptr, gi}};
+        SmlConvBwdGroup bg[3] = {{g[0], nullptr, gu, -1}, {g[1], nullptr, gi, -1}, {g[2], nullptr, gi, -1}};
         rc = sml_launch_conv_bwd(bg, 3, a->variant, w.dA, 0.f, nullptr, st);
         if (rc) return rc;
     }
@@ -515,8 +515,11 @@ int sml_run_mf_grads(const sml_step_args *a, float *d_rows, float *scores, void 
     SmlRowGroup g[3];
     make_groups(a, g);
     float *gu = a->g_theta, *gi = a->g_theta ? a->g_theta + SML_NET_STRIDE : nullptr;
-    SmlConvBwdGroup bg[3] = {{g[0], nullptr, gu}, {g[1], nullptr, gi}, {g[2], nullptr, gi}};
-    // d_rows uses the step row layout (sml_step_rows): user rows at 0, positives at row_pos, negatives at row_neg
+    // d_rows uses the step row layout (sml_step_rows): user rows at 0, positives at row_pos, negatives at row_neg -- or, with
+    // d_rows_by_id, the order of the gathered ids (both item groups index the [2 * batch] rows that start at row_pos)
+    const Rows r = rows_of(a->batch);
+    const int64_t bu = a->d_rows_by_id ? 0 : -1, bi = a->d_rows_by_id ? r.Bp : -1;
+    SmlConvBwdGroup bg[3] = {{g[0], nullptr, gu, bu}, {g[1], nullptr, gi, bi}, {g[2], nullptr, gi, bi}};
     return sml_launch_conv_bwd(bg, 3, a->variant, w.dA, 0.f, d_rows, st);
 }
 

@@ -169,7 +169,8 @@ def step_rows(batch):
 def make_step_args(*, user, item, neg, last_user, last_item, hat_user, hat_item, theta, variant=VARIANT_COM, loss=LOSS_BCE,
                    g_user=None, g_item=None, m_user=None, v_user=None, m_item=None, v_item=None, adam_state=None,
                    lr=0.0, l2=0.0, g_theta=None, m_theta=None, v_theta=None, loss_out=None, workspace=None, batch=None,
-                   table_pitch=0, n_users=None, n_items=None, stamp_user=None, stamp_item=None, adaptive_beta=0.0, clip_max_norm=0.0):
+                   table_pitch=0, n_users=None, n_items=None, stamp_user=None, stamp_item=None, adaptive_beta=0.0, clip_max_norm=0.0,
+                   d_rows_by_id=False):
     a = StepArgs()
     B = user.numel() if batch is None else int(batch)
     a.user, a.item, a.neg, a.batch = ptr(_i64(user, "user")), ptr(_i64(item, "item")), ptr(_i64(neg, "neg")), B
@@ -187,6 +188,7 @@ def make_step_args(*, user, item, neg, last_user, last_item, hat_user, hat_item,
     a.stamp_user = ptr(stamp_user if stamp_user is None else _i32t(stamp_user, "stamp_user"))
     a.stamp_item = ptr(stamp_item if stamp_item is None else _i32t(stamp_item, "stamp_item"))
     a.adaptive_beta, a.clip_max_norm = float(adaptive_beta), float(clip_max_norm)
+    a.d_rows_by_id = int(bool(d_rows_by_id))
     if workspace is None:
         workspace = step_workspace(B, user.device)
     a.loss_out, a.workspace, a.workspace_bytes = ptr(loss_out), ptr(workspace), workspace.numel()

@@ -154,16 +154,18 @@ class RowExchange(object):
             plans.append(p)
         return plans
 
-    def fetch(self, plan, gather_fn):
-        """gather_fn(local_rows) -> [m, W] rows of this rank's shard; returns [n, W] in the original id order."""
+    def fetch(self, plan, gather_fn, permute=True):
+        """gather_fn(local_rows) -> [m, W] rows of this rank's shard; returns [n, W] in the original id order, or
+        (``permute=False``) as received, grouped by owner: row k of the request then sits at ``plan.inverse[k]`` -- consumers
+        that gather through an id list take ``plan.inverse`` as that list and save the [n, W] index copy."""
         mine = gather_fn(plan.recv_loc)
         got = self._a2a(mine, plan.recv_counts, plan.send_counts, tag="rows")
-        return got[plan.inverse]
+        return got[plan.inverse] if permute else got
 
-    def push(self, plan, rows, scatter_fn):
-        """rows: [n, W] per-id payload (row gradients) in the original id order; scatter_fn(local_rows, payload)
-        is called once on the owner side with everything this rank received."""
-        recv = self._a2a(rows[plan.order], plan.send_counts, plan.recv_counts, tag="grads")
+    def push(self, plan, rows, scatter_fn, ordered=False):
+        """rows: [n, W] per-id payload (row gradients) in the original id order -- or (``ordered``) already in send order,
+        grouped by owner; scatter_fn(local_rows, payload) is called once on the owner side with everything this rank received."""
+        recv = self._a2a(rows if ordered else rows[plan.order], plan.send_counts, plan.recv_counts, tag="grads")
         scatter_fn(plan.recv_loc, recv)
 
 
@@ -230,18 +232,20 @@ class ShardedSML(object):
         if live:
             ops.adam_rows(self.user, self.m_user, self.v_user, None, self.stamp_user, pu.recv_loc, self.mf_state, apply=False)
             ops.adam_rows(self.item, self.m_item, self.v_item, None, self.stamp_item, pi.recv_loc, self.mf_state, apply=False)
-        ru = self.ex.fetch(pu, lambda loc: ops.gather_pairs(self.last_user, hat_u, loc))      # [B, 128]
-        ri = self.ex.fetch(pi, lambda loc: ops.gather_pairs(self.last_item, hat_i, loc))      # [2B, 128]
-        ar = torch.arange(2 * B, dtype=torch.int64, device=user.device)
+        # the received [last | hat] pairs stay in arrival order (grouped by owner): the step kernels gather them through the
+        # exchange plan's inverse permutation, like they gather table rows through batch ids (no [n, 128] index copy)
+        ru = self.ex.fetch(pu, lambda loc: ops.gather_pairs(self.last_user, hat_u, loc), permute=False)      # [B, 128]
+        ri = self.ex.fetch(pi, lambda loc: ops.gather_pairs(self.last_item, hat_i, loc), permute=False)      # [2B, 128]
+        iu, ii = pu.inverse.contiguous(), pi.inverse.contiguous()
         total, rp, rn = ops.step_rows(B)
         d_rows = torch.empty(total, 64, dtype=torch.float32, device=user.device)
         if want_theta_grad:
             self.transfer.theta_grad.zero_()
-        a = ops.make_step_args(user=ar[:B], item=ar[:B], neg=ar[B:], last_user=ru, last_item=ri, hat_user=ru[:, 64:], hat_item=ri[:, 64:],
+        a = ops.make_step_args(user=iu, item=ii[:B], neg=ii[B:], last_user=ru, last_item=ri, hat_user=ru[:, 64:], hat_item=ri[:, 64:],
                                theta=self.transfer.theta, variant=self.transfer.variant, loss=ops.LOSS_BCE,
                                g_theta=self.transfer.theta_grad if want_theta_grad else None, loss_out=self.loss,
-                               workspace=self._workspace(B), table_pitch=128, n_users=B, n_items=2 * B)
-        ops.run_mf_grads(a, d_rows=d_rows)
+                               workspace=self._workspace(B), table_pitch=128, n_users=B, n_items=2 * B, d_rows_by_id=True)
+        ops.run_mf_grads(a, d_rows=d_rows)               # d_rows[:B] / d_rows[rp:rp + 2B] come out in send order
         return pu, pi, d_rows, rp
 
     # ------------------------------------------------------------------ the two hot loops
@@ -293,8 +297,9 @@ class ShardedSML(object):
         ops.adam_tick(self.mf_state, self.mf_lr)
         self._pending += 1
         pu, pi, d_rows, rp = self._forward_backward(user, item, neg, self.user, self.item, False, live=True, plans=plans)
-        self.ex.push(pu, d_rows[:B], lambda loc, g: ops.scatter_grads(self.g_user, self.user, loc, g.contiguous(), scale, self.l2))
-        self.ex.push(pi, d_rows[rp:rp + 2 * B], lambda loc, g: ops.scatter_grads(self.g_item, self.item, loc, g.contiguous(), scale, self.l2))
+        self.ex.push(pu, d_rows[:B], lambda loc, g: ops.scatter_grads(self.g_user, self.user, loc, g.contiguous(), scale, self.l2), ordered=True)
+        self.ex.push(pi, d_rows[rp:rp + 2 * B], lambda loc, g: ops.scatter_grads(self.g_item, self.item, loc, g.contiguous(), scale, self.l2),
+                     ordered=True)
         ops.adam_rows(self.user, self.m_user, self.v_user, self.g_user, self.stamp_user, pu.recv_loc, self.mf_state, apply=True)
         ops.adam_rows(self.item, self.m_item, self.v_item, self.g_item, self.stamp_item, pi.recv_loc, self.mf_state, apply=True)
         return self.loss[0] * scale

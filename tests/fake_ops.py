@@ -128,8 +128,12 @@ def run_mf_grads(a, d_rows=None, scores=None):
                                   ri[j, :64], ri[j, 64:], BCE=True, variant="com")
     B = len(u)
     _, rp, rn = step_rows(B)
-    d_rows[:B] = torch.from_numpy(r["d_u_hat"]); d_rows[rp:rp + B] = torch.from_numpy(r["d_i_hat"])
-    d_rows[rn:rn + B] = torch.from_numpy(r["d_j_hat"])
+    if a.get("d_rows_by_id"):                          # the row gathered through id k writes d_rows[k] / d_rows[rp + k]
+        d_rows[torch.from_numpy(u)] = torch.from_numpy(r["d_u_hat"])
+        d_rows[rp + torch.from_numpy(i)] = torch.from_numpy(r["d_i_hat"]); d_rows[rp + torch.from_numpy(j)] = torch.from_numpy(r["d_j_hat"])
+    else:
+        d_rows[:B] = torch.from_numpy(r["d_u_hat"]); d_rows[rp:rp + B] = torch.from_numpy(r["d_i_hat"])
+        d_rows[rn:rn + B] = torch.from_numpy(r["d_j_hat"])
     a["loss_out"][0] = float(r["loss"])
     if a["g_theta"] is not None:                       # accumulate like the kernels do (the caller zeroed it)
         gt = _np(a["g_theta"])
