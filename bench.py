@@ -81,7 +81,11 @@ def synth_periods(n, shape, seed):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock, power and throttle reasons of one GPU DURING the timed region (B200_PROFILING.md recipe: what
+    `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.*` reports), read through NVML in this
+    process every 250 ms.  A spawned `nvidia-smi -lms` poller enumerates every GPU of the box on every sample: at 8 ranks it
+    was measured to stall the work submission of the GPU it watches (transfer epochs 192 -> 223 ms with one poller, 412 ms
+    with eight); it remains the fallback when the NVML binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -90,8 +94,30 @@ class ClockSampler(threading.Thread):
         self.gpu_index = gpu_index
         self.lines = []
         self.proc = None
+        self.source = "nvml"
+        self._halt = threading.Event()
+
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.gpu_index)
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self._halt.is_set():
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+            r = int(get_reasons(h))
+            f = [str(self.gpu_index), str(sm), str(mx), "%.2f" % pw, hex(r)] + ["Active" if r & b else "Not Active" for _, b in bits]
+            self.lines.append(", ".join(f))
+            self._halt.wait(0.25)
 
     def run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            self.source = "nvidia-smi"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "250"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -101,6 +127,7 @@ class ClockSampler(threading.Thread):
             pass
 
     def stop(self):
+        self._halt.set()
         if self.proc is not None:
             self.proc.terminate()
         self.join(timeout=2)
@@ -120,7 +147,7 @@ class ClockSampler(threading.Thread):
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         busy = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
         return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
-                "power_w_max": float(max(power))}
+                "power_w_max": float(max(power)), "source": self.source}
 
 
 # --------------------------------------------------------------------------------------------
@@ -548,8 +575,7 @@ def run_ours(a):
         if world > 1:
             dist.barrier()
         meta.events.enabled = True
-        # rank 0 samples its own GPU (it prints the line).  One nvidia-smi poller per rank was measured to stall the other ranks' work
-        # submission at 8 GPUs (NVML queries from 8 processes serialise in the driver: transfer epochs 192 -> 412 ms on rank 0)
+        # rank 0 samples its own GPU (it prints the line)
         sampler = ClockSampler(local) if rank == 0 else None
         if sampler is not None:
             sampler.start()

@@ -13,7 +13,7 @@ so = sys.argv[1] if len(sys.argv) > 1 else "sml_b200/libsml_b200.so"
 out = subprocess.run(["cuobjdump", "-sass", so], stdout=subprocess.PIPE, text=True).stdout
 pats = [("UTCHMMA", r"\bUTCHMMA"), ("LDTM", r"\bLDTM"), ("STTM", r"\bSTTM"), ("UTCBAR", r"\bUTCBAR"), ("UBLKCP", r"\bUBLKCP"),
         ("UTMALDG", r"\bUTMALDG"), ("LDGSTS", r"\bLDGSTS"), ("SYNCS", r"\bSYNCS"), ("RED", r"\bRED\."), ("ATOM", r"\bATOM[GS]?\."),
-        ("LDG.128", r"\bLDG\.E\.(?:\w+\.)*128"), ("STG.128", r"\bSTG\.E\.(?:\w+\.)*128"), ("MUFU", r"\bMUFU"), ("FFMA", r"\bFFMA"), ("total", r"^\s+/\*[0-9a-f]{4}\*/")]
+        ("LDG.128", r"\bLDG\.E\.(?:\w+\.)*128"), ("STG.128", r"\bSTG\.E\.(?:\w+\.)*128"), ("MUFU", r"\bMUFU"), ("FFMA", r"\bFFMA"), ("total", r"^\s+/\*[0-9a-f]{4,}\*/\s+[A-Z@]")]
 counts = collections.OrderedDict()
 name = None
 for line in out.splitlines():
