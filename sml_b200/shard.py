@@ -162,6 +162,29 @@ class RowExchange(object):
         got = self._a2a(mine, plan.recv_counts, plan.send_counts, tag="rows")
         return got[plan.inverse] if permute else got
 
+    def fetch_async(self, plan, gather_fn):
+        """Start a fetch (un-permuted, see ``fetch``) without making the current stream wait for it: the gather runs on the
+        current stream, the all-to-all on the communicator's own stream, overlapping whatever is enqueued next.
+        -> (rows as received, handle for ``fetch_wait``).  Only for tables that nothing enqueued in between modifies."""
+        mine = gather_fn(plan.recv_loc)
+        out = mine.new_empty((int(sum(plan.send_counts)),) + tuple(mine.shape[1:]))
+        if self.world == 1:
+            out.copy_(mine)
+            return out, None
+        row_bytes = mine.element_size() * (mine[0].numel() if mine.shape[0] else 1)
+        to_peers = (int(sum(plan.recv_counts)) - int(plan.recv_counts[self.rank])) * row_bytes
+        work = dist.all_to_all_single(out, mine.contiguous(), output_split_sizes=list(plan.send_counts), input_split_sizes=list(plan.recv_counts),
+                                      group=self.group, async_op=True)
+        return out, (work, mine, to_peers)
+
+    def fetch_wait(self, handle):
+        """Make the current stream wait for a ``fetch_async``; the timer brackets only the part of it that was NOT hidden."""
+        if handle is None:
+            return
+        work, _, to_peers = handle
+        with self.comm("rows", to_peers):
+            work.wait()
+
     def push(self, plan, rows, scatter_fn, ordered=False):
         """rows: [n, W] per-id payload (row gradients) in the original id order -- or (``ordered``) already in send order,
         grouped by owner; scatter_fn(local_rows, payload) is called once on the owner side with everything this rank received."""
@@ -223,9 +246,18 @@ class ShardedSML(object):
         dist.all_reduce(t, group=self.group)
         return int(t.item())
 
-    def _forward_backward(self, user, item, neg, hat_u, hat_i, want_theta_grad, live=False, plans=None):
+    def _prefetch(self, plans, hat_u, hat_i):
+        """Start the row exchange of a later step (snapshot tables only: nothing may write them before the step runs)."""
+        ops = self.ops
+        pu, pi = plans
+        ru, hu = self.ex.fetch_async(pu, lambda loc: ops.gather_pairs(self.last_user, hat_u, loc))
+        ri, hi = self.ex.fetch_async(pi, lambda loc: ops.gather_pairs(self.last_item, hat_i, loc))
+        return ru, ri, hu, hi
+
+    def _forward_backward(self, user, item, neg, hat_u, hat_i, want_theta_grad, live=False, plans=None, rows=None):
         """Exchange rows, run forward + loss + gradients on the received [last | hat] pairs.  ``live``: hat_* are the
-        live MF shards, whose requested rows first catch up with the zero-gradient Adam steps they missed."""
+        live MF shards, whose requested rows first catch up with the zero-gradient Adam steps they missed.  ``rows``: the
+        result of an earlier ``_prefetch`` of this step's plans (the exchange then overlapped the previous step)."""
         ops = self.ops
         B = user.numel()
         pu, pi = plans if plans is not None else (self.ex.plan(user), self.ex.plan(torch.cat([item, neg])))
@@ -234,8 +266,12 @@ class ShardedSML(object):
             ops.adam_rows(self.item, self.m_item, self.v_item, None, self.stamp_item, pi.recv_loc, self.mf_state, apply=False)
         # the received [last | hat] pairs stay in arrival order (grouped by owner): the step kernels gather them through the
         # exchange plan's inverse permutation, like they gather table rows through batch ids (no [n, 128] index copy)
-        ru = self.ex.fetch(pu, lambda loc: ops.gather_pairs(self.last_user, hat_u, loc), permute=False)      # [B, 128]
-        ri = self.ex.fetch(pi, lambda loc: ops.gather_pairs(self.last_item, hat_i, loc), permute=False)      # [2B, 128]
+        if rows is not None:
+            ru, ri, hu, hi = rows
+            self.ex.fetch_wait(hu); self.ex.fetch_wait(hi)
+        else:
+            ru = self.ex.fetch(pu, lambda loc: ops.gather_pairs(self.last_user, hat_u, loc), permute=False)      # [B, 128]
+            ri = self.ex.fetch(pi, lambda loc: ops.gather_pairs(self.last_item, hat_i, loc), permute=False)      # [2B, 128]
         iu, ii = pu.inverse.contiguous(), pi.inverse.contiguous()
         total, rp, rn = ops.step_rows(B)
         d_rows = torch.empty(total, 64, dtype=torch.float32, device=user.device)
@@ -278,12 +314,16 @@ class ShardedSML(object):
         return total
 
     def tr_epoch(self, user, item, neg, B):
-        """HOT LOOP B over this rank's triples (see mf_epoch)."""
+        """HOT LOOP B over this rank's triples (see mf_epoch).  The transfer step reads snapshot tables that no step writes, so
+        the row exchange of step s + 1 is started before step s computes and runs under it (model/transfer.py:701-728 has no
+        such dependency either: only theta changes between steps)."""
         sizes, pu, pi, scales = self._epoch_plans(user, item, neg, B)
         total = torch.zeros((), dtype=torch.float32, device=user.device)
+        nxt = self._prefetch((pu[0], pi[0]), self.user_hat, self.item_hat) if sizes else None
         for s, b in enumerate(sizes):
             o = s * B
-            total += self.tr_step(user[o:o + b], item[o:o + b], neg[o:o + b], plans=(pu[s], pi[s]), scale=scales[s])
+            cur, nxt = nxt, (self._prefetch((pu[s + 1], pi[s + 1]), self.user_hat, self.item_hat) if s + 1 < len(sizes) else None)
+            total += self.tr_step(user[o:o + b], item[o:o + b], neg[o:o + b], plans=(pu[s], pi[s]), scale=scales[s], rows=cur)
         return total
 
     def mf_step(self, user, item, neg, plans=None, scale=None):
@@ -311,13 +351,13 @@ class ShardedSML(object):
             self.ops.adam_flush(self.item, self.m_item, self.v_item, self.stamp_item, self.mf_state)
             self._pending = 0
 
-    def tr_step(self, user, item, neg, plans=None, scale=None):
+    def tr_step(self, user, item, neg, plans=None, scale=None, rows=None):
         """HOT LOOP B body (model/transfer.py:701-728): theta gradients, all-reduced, replicated Adam."""
         ops = self.ops
         B = user.numel()
         if scale is None:
             scale = B / self._global_batch(B)
-        self._forward_backward(user, item, neg, self.user_hat, self.item_hat, True, plans=plans)
+        self._forward_backward(user, item, neg, self.user_hat, self.item_hat, True, plans=plans, rows=rows)
         g = self.transfer.theta_grad
         if scale != 1.0:
             g.mul_(scale)
