@@ -212,7 +212,9 @@ class meta_train(object):
         # device->host copy (flush_deferred).  The host therefore runs ahead of the GPU inside a period and its sampling work hides
         # behind the epoch graphs.  SML_DEFER=0 reads every value where the reference does (prints appear immediately).
         self.defer = os.environ.get("SML_DEFER", "1") != "0"
-        self._pending = []                         # [(device tensor, post-processing)] values still on the device
+        self._pending = {}                         # handle -> (device tensor, post-processing): values still on the device
+        self._resolved = {}                        # handle -> host value (until the end of the period)
+        self._handle = 0
         self._later_q = []                         # [callable(values)] consumers, in program order
         self._stage_depth = 0                      # > 0 inside train_one_stage3 (which flushes once, at its end)
 
@@ -394,13 +396,16 @@ class meta_train(object):
 
     # ------------------------------------------------------------------ deferred reads
     def _defer_value(self, dev_tensor, post=None):
-        """Keep a small result on the device; -> handle.  After flush_deferred ``values[handle]`` = post(host float32 tensor)."""
-        self._pending.append((dev_tensor.detach().reshape(-1).float(), post))
-        return len(self._pending) - 1
+        """Keep a small result on the device; -> handle.  After flush_deferred ``values[handle]`` = post(host float32 tensor).
+        Handles stay valid until the end of the period (or of the directly called *_onestage method)."""
+        self._handle += 1
+        self._pending[self._handle] = (dev_tensor.detach().reshape(-1).float(), post)
+        return self._handle
 
     def _const_value(self, value):
-        self._pending.append((None, value))
-        return len(self._pending) - 1
+        self._handle += 1
+        self._resolved[self._handle] = value
+        return self._handle
 
     def _print(self, *a):
         """print, in order with the deferred consumers."""
@@ -410,26 +415,24 @@ class meta_train(object):
         """Queue a consumer of deferred values (print, writer call, list append); runs at once when ``defer`` is off."""
         self._later_q.append(fn)
         if not self.defer:
-            self.flush_deferred()
+            self.flush_deferred(final=False)
 
-    def flush_deferred(self):
-        """One device->host copy of every pending value, then the queued consumers in program order."""
-        if not self._pending and not self._later_q:
-            return
+    def flush_deferred(self, final=True):
+        """One device->host copy of every pending value, then the queued consumers in program order.  ``final``: no handle
+        issued so far will be used again (end of a period): the resolved values are dropped."""
         pend, q = self._pending, self._later_q
-        self._pending, self._later_q = [], []
-        devs = [t for t, _ in pend if t is not None]
-        host = torch.cat(devs).cpu() if devs else None
-        vals, off = [], 0
-        for t, post in pend:
-            if t is None:
-                vals.append(post)
-                continue
-            h = host[off:off + t.numel()]
-            off += t.numel()
-            vals.append(post(h) if post is not None else h)
+        self._pending, self._later_q = {}, []
+        if pend:
+            host = torch.cat([t for t, _ in pend.values()]).cpu()
+            off = 0
+            for h, (t, post) in pend.items():
+                x = host[off:off + t.numel()]
+                off += t.numel()
+                self._resolved[h] = post(x) if post is not None else x
         for fn in q:
-            fn(vals)
+            fn(self._resolved)
+        if final:
+            self._resolved = {}
 
     def invalidate(self):
         """Call after writing the MF tables from OUTSIDE this class through a path torch cannot see
@@ -617,8 +620,9 @@ class meta_train(object):
 
     def _scaled(self, h, k):
         """Handle of k * (the deferred scalar behind handle h)."""
-        self._pending.append((None, None))
-        hs = len(self._pending) - 1
+        self._handle += 1
+        hs = self._handle
+
         def fill(v, h=h, hs=hs, k=k):
             v[hs] = v[h] * k
         self._later_q.append(fill)

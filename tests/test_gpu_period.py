@@ -12,7 +12,7 @@ from tests.test_host_logic import make_args, write_fixture_stream
 pytestmark = pytest.mark.gpu
 
 
-def run_ours(g, tmp, stop, replay, news=False, opts=False):
+def run_ours(g, tmp, stop, replay, news=False, opts=False, defer=True):
     from sml_b200.data.dataset2 import transfer_data
     from sml_b200.model.transfer import meta_train
     NP, U, I = write_fixture_stream(g, tmp)
@@ -35,6 +35,7 @@ def run_ours(g, tmp, stop, replay, news=False, opts=False):
             assert k == kind and len(tri) == n_rows
             return tri[:, 0].copy(), tri[:, 1].copy(), tri[:, 2].copy()
     meta = meta_train(args, ds, U, I, 64, batch_source=src)
+    meta.defer = defer
     tu, ti = theta_from_chk(g["theta_com"])
     sd = {("user_transfer." + k): torch.from_numpy(v) for k, v in tu.items()}
     sd.update({("item_transfer." + k): torch.from_numpy(v) for k, v in ti.items()})
@@ -140,3 +141,17 @@ def test_first_period_within_tolerance(golden, tmp_path, name):
     assert abs(float(iw.abs().sum()) - ref[3]) < 1e-4 * ref[3]
     assert abs(th - ref[4]) < 1e-4 * ref[4]
     assert abs(float(uw.sum()) - ref[0]) < 1e-4 * ref[1] and abs(float(iw.sum()) - ref[2]) < 1e-4 * ref[3]
+
+
+def test_blocking_reads_give_the_same_run(golden, tmp_path):
+    """SML_DEFER=0 (a blocking read at every print, like the reference) and the default (one read per period) enqueue the
+    same kernels in the same order: bit-identical tables, metric lists and evaluation log."""
+    g = golden("period_run")
+    a = run_ours(g, str(tmp_path / "a"), False, True, defer=True)
+    b = run_ours(g, str(tmp_path / "b"), False, True, defer=False)
+    assert torch.equal(a.MFbase.user_laten.weight.data, b.MFbase.user_laten.weight.data)
+    assert torch.equal(a.MFbase.item_laten.weight.data, b.MFbase.item_laten.weight.data)
+    assert torch.equal(a.transfer.theta, b.transfer.theta)
+    assert a.eval_log == b.eval_log and len(a.eval_log) == len(g["eval_log"])
+    assert a.recall == b.recall and [float(x) for x in a.ndcg] == [float(x) for x in b.ndcg]
+    assert a.last_MF_loss == b.last_MF_loss and a.last_TR_loss == b.last_TR_loss

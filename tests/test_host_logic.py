@@ -262,7 +262,7 @@ def test_eval_cache_never_serves_stale_ranks(monkeypatch):
     w = lambda: types.SimpleNamespace(weight=torch.nn.Parameter(torch.zeros(2, 2)))
     m.MFbase = types.SimpleNamespace(user_laten=w(), item_laten=w(), eval=lambda: None)
     m._tab_version, m._eval_cache = 0, None
-    m.defer, m._pending, m._later_q, m._stage_depth = True, [], [], 0
+    m.defer, m._pending, m._resolved, m._handle, m._later_q, m._stage_depth = True, {}, {}, 0, [], 0
     m.eval_passes = dict(scored=0, reused=0)
     m.events = EventTimers(False)
     m.timers = dict(eval=0.0)
@@ -305,3 +305,50 @@ def test_eval_cache_never_serves_stale_ranks(monkeypatch):
     m._eval(ts, 20); assert m.eval_passes["scored"] == 33
     m.invalidate()
     m._eval(ts, 20); assert m.eval_passes["scored"] == 34
+
+
+def test_deferred_reads_keep_the_reference_print_order(golden, tmp_path, capsys):
+    """meta_train reads losses / metrics back once per period (flush_deferred): the period's prints, list appends and loss
+    attributes must come out exactly as with a blocking read at every print (SML_DEFER=0, the reference's behaviour), in the
+    same order, and nothing may be left queued when train_one_stage3 returns."""
+    g = golden("period_run")
+    tmp = str(tmp_path)
+    NP, U, I = write_fixture_stream(g, tmp)
+    outs = []
+    for defer in (True, False):
+        args = make_args(g, tmp, False)
+        torch.manual_seed(args.seed); np.random.seed(args.seed + 2)
+        ds = transfer_data(args, path=args.data_path, datasetname="mini", file_path_list=[str(i) for i in range(NP)],
+                           test_list=[str(j) for j in range(5, NP)], validation_list=None, online_train_time=2, online_test_time=5)
+        probe = HostProbe(args, ds, U, I, 64)
+        probe.defer = defer
+        n = [0]
+        ev, mf, tr = probe._eval, probe._mf_epoch, probe._tr_epoch
+
+        def eval_(test_set, topK, ev=ev, n=n):                # distinct values so that a swapped pair would show
+            ev(test_set, topK)
+            n[0] += 1
+            return probe._const_value((n[0] / 1000.0, torch.tensor(n[0] / 500.0)))
+
+        def mf_(a, t, mf=mf, n=n):
+            mf(a, t)
+            n[0] += 1
+            return probe._const_value(n[0] * 1.5)
+
+        def tr_(a, t, tr=tr, n=n):
+            tr(a, t)
+            n[0] += 1
+            return probe._const_value(n[0] * 2.5)
+        probe._eval, probe._mf_epoch, probe._tr_epoch = eval_, mf_, tr_
+        capsys.readouterr()
+        stage, seen = 0, []
+        while probe.train_one_stage3(args, stage):
+            assert not probe._pending and not probe._later_q          # flushed at the end of every period
+            seen.append((len(probe.recall), getattr(probe, "last_MF_loss", None), getattr(probe, "last_TR_loss", None)))
+            stage += 1
+        text = capsys.readouterr().out
+        # dataset constructors print while they run ("user max: ..."): not part of the deferred stream
+        lines = [ln for ln in text.splitlines() if not ln.startswith("user max") and "time cost" not in ln]
+        outs.append((lines, seen, [float(x) for x in probe.recall], [float(x) for x in probe.ndcg_5]))
+    assert outs[0][0] == outs[1][0] and len(outs[0][0]) > 50
+    assert outs[0][1:] == outs[1][1:] and len(outs[0][2]) == 3
