@@ -145,13 +145,16 @@ def test_first_period_within_tolerance(golden, tmp_path, name):
 
 def test_blocking_reads_give_the_same_run(golden, tmp_path):
     """SML_DEFER=0 (a blocking read at every print, like the reference) and the default (one read per period) enqueue the
-    same kernels in the same order: bit-identical tables, metric lists and evaluation log."""
+    same kernels in the same order: the same run up to the run-to-run noise of the fp32 atomics (split-K sums, scatter-adds),
+    which Adam amplifies over the ~100 steps of the stream like it does between any two runs."""
     g = golden("period_run")
     a = run_ours(g, str(tmp_path / "a"), False, True, defer=True)
     b = run_ours(g, str(tmp_path / "b"), False, True, defer=False)
-    assert torch.equal(a.MFbase.user_laten.weight.data, b.MFbase.user_laten.weight.data)
-    assert torch.equal(a.MFbase.item_laten.weight.data, b.MFbase.item_laten.weight.data)
-    assert torch.equal(a.transfer.theta, b.transfer.theta)
-    assert a.eval_log == b.eval_log and len(a.eval_log) == len(g["eval_log"])
-    assert a.recall == b.recall and [float(x) for x in a.ndcg] == [float(x) for x in b.ndcg]
-    assert a.last_MF_loss == b.last_MF_loss and a.last_TR_loss == b.last_TR_loss
+    for x, y in ((a.MFbase.user_laten.weight.data, b.MFbase.user_laten.weight.data), (a.MFbase.item_laten.weight.data, b.MFbase.item_laten.weight.data),
+                 (a.transfer.theta, b.transfer.theta)):
+        assert float((x - y).abs().max()) <= 2e-3 * float(y.abs().max())
+    la, lb = np.array(a.eval_log), np.array(b.eval_log)
+    assert la.shape == lb.shape == g["eval_log"].shape and np.array_equal(la[:, :2], lb[:, :2])       # same calls in the same order
+    assert np.abs(la[:, 2] - lb[:, 2]).max() <= 2.0 / 96 + 1e-9 and np.abs(la[:, 3] - lb[:, 3]).max() <= 2e-2
+    assert len(a.recall) == len(b.recall) == 3 and np.abs(np.array(a.recall) - np.array(b.recall)).max() <= 2.0 / 96 + 1e-9
+    assert abs(a.last_MF_loss - b.last_MF_loss) <= 1e-3 * abs(b.last_MF_loss) and abs(a.last_TR_loss - b.last_TR_loss) <= 1e-3 * abs(b.last_TR_loss)
