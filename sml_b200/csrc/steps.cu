@@ -94,8 +94,12 @@ void make_groups(const sml_step_args *a, SmlRowGroup g[3]) {
 
 // K = 512 GEMMs (fc2, d1) of small batches have only a handful of output tiles: slice K so they cover more SMs
 // (measured: 119.3 -> 117.0 us for the B = 256 transfer step; at B = 1024 the atomics cost more than the slicing gains)
+// (d1, which = 1: with the two weight-gradient GEMMs on their own streams the tail of the transfer step is bound by the number of
+// one-CTA-per-SM tiles in flight, and an unsliced d1 -- 30 tiles instead of 120, no atomics -- wins: tools/ksplit_sweep.py, 65.1 -> 61.8 us
+// together with dW1 in 2 slices)
 int step_ksplit(const Rows &r, int which = 0) {
     if (sml_debug_ksplit(which) > 0) return sml_debug_ksplit(which);
+    if (which == 1) return 1;
     return (r.user_tiles + r.item_tiles) <= 12 ? 4 : 1;
 }
 
@@ -121,8 +125,8 @@ void pk_pair(SmlPkProb out[2], const Rows &r, const uint8_t *A, int KC, size_t w
 // profiles/r01_tr_step_breakdown.md).  Event record / wait are stream-capturable, so inside a CUDA graph this becomes
 // two parallel branches.
 struct SideStream {
-    cudaStream_t s = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, join2 = nullptr;
+    cudaStream_t s = nullptr, s2 = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, fork2 = nullptr, join2 = nullptr, join3 = nullptr;
 };
 SideStream *side_stream() {
     static SideStream per_dev[64];
@@ -131,6 +135,8 @@ SideStream *side_stream() {
     SideStream &x = per_dev[dev];
     if (!x.s) {
         if (cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithFlags(&x.s2, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&x.join3, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         if (cudaEventCreateWithFlags(&x.fork2, cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -293,7 +299,7 @@ int fc1_wgrad(const sml_step_args *a, const StepWs &w, float *g_theta, cudaStrea
         {w.dZ1 + Bp * 512, w.A + Bp * 320, nullptr, nullptr, gi + SML_OFF_F1W, 512, 320, (int)(2 * B), 512, 320, 320}};
     if (sml_use_tensor_cores())
         rc = sml_launch_umma_gemm(w1, 2, SML_A_KM, SML_B_KN, SML_EPI_ACCUM, 0, 64, st,
-                                  sml_debug_ksplit(3) > 0 ? sml_debug_ksplit(3) : (ksplit > 2 ? ksplit / 2 : 1));
+                                  sml_debug_ksplit(3) > 0 ? sml_debug_ksplit(3) : (B >= 2048 ? ksplit / 2 : (ksplit > 2 ? ksplit / 4 : 1)));
     else rc = sml_launch_sgemm(w1, 2, SML_A_KM, SML_B_KN, SML_EPI_ACCUM, st);
     if (rc) return rc;
     if (sml_use_tensor_cores()) return SML_OK;     // bias gradients already accumulated by k_loss and the d2 epilogue
@@ -465,11 +471,18 @@ int sml_tr_step(const sml_step_args *a, void *stream) {
     const int dbg = sml_debug_mask();
     if (dbg & (4 | 8 | 128 | 256)) return SML_OK;
     if (!(dbg & 1)) {
+        // branches 1a / 1b: dW1 and dW2 are independent of each other: each on its own side stream (in the CUDA graph: two more
+        // parallel branches).  One after the other they ended 8 us after the main branch (tools/tr_timeline.py: dW2 34 -> 48 us,
+        // dW1 48 -> 61 us, conv backward done at 53 us) and held up the Adam update.
         SML_CUDA_OK(cudaEventRecord(ss->fork, st));
         SML_CUDA_OK(cudaStreamWaitEvent(ss->s, ss->fork, 0));
-        rc = fc_wgrads(a, w, a->g_theta, ss->s);                           // branch 1: dW2, dW1 (+ bias sums on the SIMT path)
+        SML_CUDA_OK(cudaStreamWaitEvent(ss->s2, ss->fork, 0));
+        rc = fc1_wgrad(a, w, a->g_theta, ss->s);                           // dW1 (the longer one; + bias sums on the SIMT path)
         if (rc) return rc;
         SML_CUDA_OK(cudaEventRecord(ss->join, ss->s));
+        rc = fc2_wgrad(a, w, a->g_theta, ss->s2);                          // dW2
+        if (rc) return rc;
+        SML_CUDA_OK(cudaEventRecord(ss->join3, ss->s2));
     }
     if (!(dbg & 2)) {
         rc = fc1_dgrad(a, w, st);                                          // branch 2: dA, conv backward
@@ -481,7 +494,10 @@ int sml_tr_step(const sml_step_args *a, void *stream) {
         rc = sml_launch_conv_bwd(bg, 3, a->variant, w.dA, 0.f, nullptr, st);
         if (rc) return rc;
     }
-    if (!(dbg & 1)) SML_CUDA_OK(cudaStreamWaitEvent(st, ss->join, 0));
+    if (!(dbg & 1)) {
+        SML_CUDA_OK(cudaStreamWaitEvent(st, ss->join, 0));
+        SML_CUDA_OK(cudaStreamWaitEvent(st, ss->join3, 0));
+    }
     if (dbg & 64) return SML_OK;
     // Adam with coupled L2 (weight_decay = TR_l2, model/transfer.py:393) over the whole theta block
     if (a->clip_max_norm > 0.0) {

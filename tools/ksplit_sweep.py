@@ -38,12 +38,12 @@ def timed():
 
 
 res = []
-for fc2, d1, w2, w1 in itertools.product((1, 2, 4), (1, 2, 4), (2, 4, 8), (1, 2, 4)):
+for fc2, d1, w2, w1 in itertools.product((0,), (1, 2, 4, 8), (1, 2, 4, 8, 16), (1, 2, 4, 8)):      # (fc2 is fused into fc1 at this batch size)
     ops.lib().sml_debug_set_ksplit(fc2, d1, w2, w1)
     res.append((timed(), fc2, d1, w2, w1))
 ops.lib().sml_debug_set_ksplit(0, 0, 0, 0)
 base = timed()
 res.sort()
-print("built-in choice (fc2 4, d1 4, dW2 8, dW1 4): %.1f us" % base)
-for t, fc2, d1, w2, w1 in res[:12] + res[-3:]:
+print("built-in choice (d1 4, dW2 8, dW1 4): %.1f us" % base)
+for t, fc2, d1, w2, w1 in res[:16] + res[-3:]:
     print("fc2 %d  d1 %d  dW2 %d  dW1 %d : %.1f us" % (fc2, d1, w2, w1, t))
