@@ -255,6 +255,17 @@ k_umma_packed(PkParams P) {
         }
     } else {
         // ===== epilogue warps: straight from TMEM registers, one accumulator row per thread =====
+        // d2: the Z1 values of this thread's first 32 columns (the GELU' factor of the epilogue) do not depend on the MMAs: request them
+        // now, one L2 round trip ahead of their use (the loss prologue and the MMAs run under it)
+        float4 zpre[8];
+        if (EPI == SML_PK_D2) {
+            const int pr = (warp & 3) * 32 + lane, pc0 = ((warp - 2) >> 2) * (BN / 2);
+            const bool pvalid = tile_m * 128 + pr < p.M;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                zpre[q] = pvalid ? __ldg(reinterpret_cast<const float4 *>(p.aux + (p.row0 + (int64_t)tile_m * 128 + pr) * p.ldc + tile_n * BN + pc0) + q)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         if (LOSS) {
             // ===== loss + dL/dY for the 128 rows of this tile, written as the packed A operand (two 32-column K chunks of dY) =====
             // Eight lanes per row (lane sub = lane & 7 owns columns 8 sub .. 8 sub + 7: every row is read as one coalesced 256 B
@@ -430,7 +441,8 @@ k_umma_packed(PkParams P) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (valid) z = __ldg(reinterpret_cast<const float4 *>(p.aux + m * p.ldc + nb) + q);
+                    if (c0 == chalf * (BN / 2)) z = zpre[q];
+                    else if (valid) z = __ldg(reinterpret_cast<const float4 *>(p.aux + m * p.ldc + nb) + q);
                     v[4 * q] *= sml_gelu_grad(z.x); v[4 * q + 1] *= sml_gelu_grad(z.y);
                     v[4 * q + 2] *= sml_gelu_grad(z.z); v[4 * q + 3] *= sml_gelu_grad(z.w);
                 }
