@@ -522,17 +522,21 @@ def run_ours(a):
                 dist.barrier()
             h2d[0] = 0
             t0 = time.perf_counter()
+            marks = []
             for _ in range(K):
                 # every period file crosses PCIe exactly once, when the stream first reaches it (D_{t+1} is period t's validation
                 # file and period t+1's training file); meta_train uploads it on a copy stream while the previous period computes
                 meta.train_one_stage3(args, stage); stage += 1
+                marks.append(time.perf_counter() - t0)            # (train_one_stage3 ends with the period's one blocking read)
             torch.cuda.synchronize()
             secs = time.perf_counter() - t0
+            per_period[device_sampler] = [round((b - a) * 1e3, 1) for a, b in zip([0.0] + marks[:-1], marks)]
             if world > 1:
                 t = torch.tensor([secs], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); secs = float(t)
             return secs, h2d[0] / K
 
         e2e_s, e2e_h2d, e2e_dev_s, e2e_dev_h2d = float("nan"), 0, float("nan"), 0
+        per_period = {}
         mf_steps, tr_steps, n_updata, n_evals = period_counts(shape["rows"])
         e2e_d2h = (n_evals * 8 + (HYPER["multi_num"] * (HYPER["MF_epochs"] + HYPER["TR_epochs"])) * 4)
         if not a.skip_e2e:
@@ -657,11 +661,11 @@ def run_ours(a):
         "config": bench_config(shape, world),
         "samples_per_s": world * K * (HYPER["multi_num"] * shape["rows"] * (HYPER["MF_epochs"] + HYPER["TR_epochs"])) / dev_s,
         "e2e": {"value": (world * K / e2e_s) if e2e_s == e2e_s else None, "unit": "periods/s", "h2d_bytes_per_step": int(e2e_h2d),
-                "d2h_bytes_per_step": int(e2e_d2h), "mode": "meta_train in its default mode (batches drawn on the host bit-identically to the reference, "
+                "d2h_bytes_per_step": int(e2e_d2h), "ms_per_period_rank0": per_period.get(False), "mode": "meta_train in its default mode (batches drawn on the host bit-identically to the reference, "
                         "--numworkers 0): pinned host period files, each uploaded once when the stream reaches it (copy stream, overlapping the previous "
                         "period), every epoch's sampled triples uploaded, every loss / recall / ndcg of the period read back at its end"},
         "e2e_device_sampler": {"value": (world * K / e2e_dev_s) if e2e_dev_s == e2e_dev_s else None, "unit": "periods/s",
-                               "h2d_bytes_per_step": int(e2e_dev_h2d), "d2h_bytes_per_step": int(e2e_d2h),
+                               "h2d_bytes_per_step": int(e2e_dev_h2d), "d2h_bytes_per_step": int(e2e_d2h), "ms_per_period_rank0": per_period.get(True),
                                "mode": "meta_train(device_sampler=True): shuffling and negative sampling on the GPU (Philox), only the period files cross PCIe; "
                                        "the sampling kernels run on the compute stream (~10 ms per period), the host sampler of the default mode is hidden behind it"},
         "gpu_launches": int(launches),

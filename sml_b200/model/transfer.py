@@ -191,6 +191,7 @@ class meta_train(object):
         self._ws = {}
         self._dev_cache = {}
         self._free_bufs = []                       # [(int64 device buffer, event)] period-file buffers waiting for reuse
+        self._pin_pool = []                        # [[pinned int64 staging buffer, event of its last copy]] (sampled triples -> device)
         self._buf_sizes = []                       # capacities of all pooled buffers ever allocated
         self.dev_cache_cap = 6                     # period files kept resident on the device
         self.prefetch = os.environ.get("SML_PREFETCH", "1") != "0"   # upload the next period's files during the current one (prefetch_files)
@@ -378,21 +379,44 @@ class meta_train(object):
             self._copy_stream = torch.cuda.Stream(device=self.device)
         out = []
         cur = torch.cuda.current_stream()
+        used = []
         for x in arrs:
             if isinstance(x, torch.Tensor):
                 out.append(x)
                 continue
-            a = np.ascontiguousarray(x, dtype=np.int64)
-            stage = torch.empty(a.shape, dtype=torch.int64, pin_memory=True)
-            stage.numpy()[...] = a
+            a = np.ascontiguousarray(x, dtype=np.int64).reshape(-1)
+            stage, slot = self._pinned(a.size)
+            stage[:a.size].numpy()[...] = a
             with torch.cuda.stream(self._copy_stream):
-                t = stage.to(self.device, non_blocking=True)
+                t = stage[:a.size].to(self.device, non_blocking=True).view(np.shape(x))
             t.record_stream(cur)
+            used.append(slot)
             out.append(t)
         ev = torch.cuda.Event()
         ev.record(self._copy_stream)
+        for slot in used:
+            slot[1] = ev                               # the staging buffer is free again once this copy has run
         cur.wait_event(ev)
         return out
+
+    def _pinned(self, n):
+        """Pinned staging buffer of >= n int64 from a ring owned by this object.  torch's pinned allocator would do, but a
+        NEW pinned allocation (cudaHostAlloc) synchronises the device: with the host running a whole period ahead of the GPU one
+        such call was measured to cost 60 ms (the host loses its lead and its sampling work becomes visible)."""
+        BUSY = "busy"                                  # handed out by this very _upload call, event not recorded yet
+        for slot in self._pin_pool:
+            if slot[0].numel() >= n and slot[1] is not BUSY and (slot[1] is None or slot[1].query()):
+                slot[1] = BUSY
+                return slot[0], slot
+        if len(self._pin_pool) >= 128:                 # everything in flight: wait for the oldest copy instead of growing further
+            for slot in self._pin_pool:
+                if slot[0].numel() >= n and slot[1] is not BUSY and slot[1] is not None:
+                    slot[1].synchronize()
+                    slot[1] = BUSY
+                    return slot[0], slot
+        slot = [torch.empty(max(int(n * 1.25), 1 << 16), dtype=torch.int64, pin_memory=True), BUSY]
+        self._pin_pool.append(slot)
+        return slot[0], slot
 
     # ------------------------------------------------------------------ deferred reads
     def _defer_value(self, dev_tensor, post=None):
