@@ -271,7 +271,8 @@ def reference_leg(device, scale, timeout=600):
 # --------------------------------------------------------------------------------------------
 # kernels in isolation, at sizes that stream from HBM (N = 1 only)
 # --------------------------------------------------------------------------------------------
-FUSED_FWD_NCU_DRAM_BYTES_PER_ROW = 741.4     # (dram__bytes_read.sum + dram__bytes_write.sum) / rows of k_transfer_fused, ncu --set full at 1 M rows (profiles/r02_kernels_ncu.md)
+TR_STEP_NCU_DRAM_BYTES = 30_690_000          # one transfer step (B = 256), see the roofline object
+FUSED_FWD_NCU_DRAM_BYTES_PER_ROW = 743.8     # (dram__bytes_read.sum + dram__bytes_write.sum) / rows of k_transfer_fused, ncu --set full at 1 M rows (profiles/r02_kernels_ncu.md)
 PLAIN_MF_NCU_DRAM_BYTES_PER_TRIPLE = 4780.0  # same for k_plain_mf_step at 65 536 triples per step on 20 M-row tables
 
 
@@ -678,9 +679,11 @@ def run_ours(a):
             roofline_phases["tr_epoch"], kernel="transfer step = sml_tr_step: k_pack_theta || k_conv_fwd, k_umma_packed x3 (fc1 + fc2 fused, loss + d2 fused, d1: "
             "the tcgen05 3xTF32 GEMM), k_umma_gemm x2 (weight gradients), k_conv_bwd, k_adam_dense -- %d launches of this chain per period, %.0f %% of the "
             "period's device time" % (tr_steps, 100.0 * ph_ms.get("tr_epoch", 0.0) / max(dev_s / K * 1e3, 1e-9)),
-            traffic=None, peak_source="measured cuBLAS bf16 TFLOP/s (MEASURED_PEAKS.json, burst) / 2 (tf32) / 3 (3xTF32)",
+            traffic=TR_STEP_NCU_DRAM_BYTES, traffic_note="dram__bytes_read.sum + dram__bytes_write.sum summed over the nine kernels of one step, ncu --set full, "
+            "cold single launches (profiles/r02_kernels_ncu.md); algorithmic bytes per step: 768 x 512 B of table rows + 394 688 parameters x 32 B of Adam traffic = 13.0 MB",
+            peak_source="measured cuBLAS bf16 TFLOP/s (MEASURED_PEAKS.json, burst) / 2 (tf32) / 3 (3xTF32)",
             note="achieved = 3 x 403 456 FLOP (forward, data gradient, weight gradient) x 768 rows per step / the step's device time, measured "
-                 "live (CUDA events around every transfer epoch of the timed region).  A 768-row step is 9 kernels of 4-15 us on a dependency chain of 6: "
+                 "live (CUDA events around every transfer epoch of the timed region).  A 768-row step is 9 kernels of 4-17 us on a dependency chain of 6 (three parallel branches after d2): "
                  "latency-bound, far below the tensor roofline; the same GEMM pipeline streaming rows (kernels.k_transfer_fused, the "
                  "updata kernel) reaches kernels.k_transfer_fused.frac of it.  Rooflines of the other phases: roofline_phases; of the "
                  "kernels in isolation: kernels.*"),
