@@ -108,13 +108,28 @@ __device__ __forceinline__ void sml_adam_tick_body(int64_t *state, double lr, do
 }
 
 // One element of one Adam step; shared by the dense sweep and the row-lazy replay so both round identically.
+// sqrt and the two divisions of torch's formula (denom = sqrt(v) / sqrt(bc2) + eps; p -= step_size * m / denom) use the SFU
+// approximations (sqrt.approx / rcp.approx, <= 2 ulp each) instead of the IEEE sequences: the row-lazy replay executes this
+// function once per element and MISSED step (catch-up before every batch, flush after every epoch: 28 % of the MF epochs with the
+// IEEE forms, ~40 instructions per element-step against ~12).  Effect on an update: <= ~5e-7 relative, i.e. <= 5e-9 absolute per
+// step at lr = 0.01 -- four orders of magnitude inside the 1e-4-after-a-period tolerance, the same trade as sml_gelu above.
+__device__ __forceinline__ float sml_rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sml_sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ void sml_adam1(float &p, float &m, float &v, float g, float b1c, float beta2, float b2c,
                                           float step_size, float bc2_sqrt, float eps, float wd) {
     if (wd != 0.f) g = fmaf(wd, p, g);                 // grad.add(param, alpha=weight_decay)
     m = fmaf(g - m, b1c, m);                           // exp_avg.lerp_(grad, 1 - beta1)
     v = fmaf(b2c * g, g, beta2 * v);                   // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
-    const float denom = sqrtf(v) / bc2_sqrt + eps;
-    p = p - step_size * (m / denom);                   // param.addcdiv_(exp_avg, denom, value=-step_size)
+    const float denom = fmaf(sml_sqrt_approx(v), sml_rcp_approx(bc2_sqrt), eps);
+    p = p - step_size * (m * sml_rcp_approx(denom));   // param.addcdiv_(exp_avg, denom, value=-step_size)
 }
 #endif
 
