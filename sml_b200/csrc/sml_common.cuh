@@ -113,14 +113,15 @@ __device__ __forceinline__ void sml_adam_tick_body(int64_t *state, double lr, do
 // function once per element and MISSED step (catch-up before every batch, flush after every epoch: 28 % of the MF epochs with the
 // IEEE forms, ~40 instructions per element-step against ~12).  Effect on an update: <= ~5e-7 relative, i.e. <= 5e-9 absolute per
 // step at lr = 0.01 -- four orders of magnitude inside the 1e-4-after-a-period tolerance, the same trade as sml_gelu above.
+// (.ftz: the reciprocals only ever see sqrt(bc2) in (0.03, 1] and denom >= eps = 1e-8; a subnormal v flushes to sqrt = 0 against eps.)
 __device__ __forceinline__ float sml_rcp_approx(float x) {
     float r;
-    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 __device__ __forceinline__ float sml_sqrt_approx(float x) {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 __device__ __forceinline__ void sml_adam1(float &p, float &m, float &v, float g, float b1c, float beta2, float b2c,
