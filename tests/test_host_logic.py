@@ -322,6 +322,12 @@ def test_deferred_reads_keep_the_reference_print_order(golden, tmp_path, capsys)
                            test_list=[str(j) for j in range(5, NP)], validation_list=None, online_train_time=2, online_test_time=5)
         probe = HostProbe(args, ds, U, I, 64)
         probe.defer = defer
+        scalars = []
+
+        class Writer(object):                                  # stands in for the TensorBoard writer of --need_writer
+            def add_scalar(self, name, value, itr):
+                scalars.append((name, round(float(value), 6), itr))
+        probe.need_writer, probe.writer = True, Writer()
         n = [0]
         ev, mf, tr = probe._eval, probe._mf_epoch, probe._tr_epoch
 
@@ -349,6 +355,14 @@ def test_deferred_reads_keep_the_reference_print_order(golden, tmp_path, capsys)
         text = capsys.readouterr().out
         # dataset constructors print while they run ("user max: ..."): not part of the deferred stream
         lines = [ln for ln in text.splitlines() if not ln.startswith("user max") and "time cost" not in ln]
-        outs.append((lines, seen, [float(x) for x in probe.recall], [float(x) for x in probe.ndcg_5]))
+        outs.append((lines, seen, [float(x) for x in probe.recall], [float(x) for x in probe.ndcg_5], scalars))
     assert outs[0][0] == outs[1][0] and len(outs[0][0]) > 50
     assert outs[0][1:] == outs[1][1:] and len(outs[0][2]) == 3
+    # the writer sees the reference's scalars (model/transfer.py:447-449,520-527,686-690,716,741-744) with the right iteration counters
+    sc = outs[0][4]
+    names = {n for n, _, _ in sc}
+    assert names == {"Acc/MF-recall20", "Acc/MF-ndcg20", "norm/user-norm", "Loss/MF-loss", "Acc/tr-TR-recall@20", "Acc/tr-TR-ndcg@20", "Loss/TR-loss"}
+    mf_itrs = [i for n, _, i in sc if n == "Loss/MF-loss"]
+    assert mf_itrs == sorted(mf_itrs) and len(set(mf_itrs)) == len(mf_itrs)
+    tr_loss = [v for n, v, _ in sc if n == "Loss/TR-loss"]
+    assert all(abs(v * 16 / 2.5 - round(v * 16 / 2.5)) < 1e-3 for v in tr_loss)      # = (2.5 x call number) / TR_batch_size (16)
