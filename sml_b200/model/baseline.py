@@ -254,28 +254,43 @@ class SPMF(object):
             os.makedirs(self.save_dir, exist_ok=True)
             torch.save(self.MFbase.state_dict(), os.path.join(self.save_dir, name))
 
+    def _begin_stage(self, stage_id, types):
+        """What both per-period methods do first (reference: model/baseline.py:233-245,313-326): next (train, test) pair, the
+        item universe, reservoir + new data as the training set, the user -> items index the negative samplers exclude."""
+        set_t, now_test = self.get_next_data(stage_id, types=types)
+        if set_t is None:
+            return None
+        self.test_num.append(now_test.shape[0])
+        self.all_item = np.union1d(self.all_item, set_t[:, 1])
+        have = self.Reservious.pool_have
+        train_data = np.concatenate([self.Reservious.pool[0:have], set_t], axis=0) if have > 0 else set_t
+        self.user_hit_num_in_W_R(train_data)
+        return set_t, now_test, train_data
+
+    class _Best(object):
+        """Best recall@20 so far and the evaluations since it improved (the early-stopping bookkeeping of :252-255,289-299,
+        :334-337,366-378; the reference only ever stops early on the news data, pool_init_type = 1)."""
+
+        def __init__(self):
+            self.recall20, self.recall, self.ndcg, self.stale = 0, None, None, 0
+
+        def update(self, F_recall, F_ndcg):
+            if self.recall20 < F_recall[-1]:
+                self.recall20, self.recall, self.ndcg, self.stale = F_recall[-1], F_recall, F_ndcg, 0
+
     def run_one_stage(self, stage_id):
         """SPMF, one period (reference: model/baseline.py:227-304): train on reservoir + new data with rank-weighted
         sampling, then update the reservoir."""
-        set_t, now_test = self.get_next_data(stage_id)
-        if set_t is None:
+        begun = self._begin_stage(stage_id, "only_new")
+        if begun is None:
             return False
-        self.test_num.append(now_test.shape[0])
-        self.all_item = np.union1d(self.all_item, set_t[:, 1])
-        if self.Reservious.pool_have > 0:
-            train_data = np.concatenate([self.Reservious.pool[0:self.Reservious.pool_have], set_t], axis=0)
-        else:
-            train_data = set_t
-        self.user_hit_num_in_W_R(train_data)
+        set_t, now_test, train_data = begun
         itr = round(train_data.shape[0] / self.batch_size)
         p = self.compute_R_W_P(train_data)
         print("start train...")
         F_recall, F_ndcg, _, _ = self.test(now_test)         # (the reference unpacks two of the four values here and raises, :250)
         print("before train test---", "recall(5,10,20):", F_recall, "ndcg (5,10,20):", F_ndcg)
-        max_recall20 = 0
-        max_recall = None
-        max_Ndcg = None
-        not_chang = 0
+        best = self._Best()
         T = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64).reshape(-1)).to(self.device)
         for epoch in range(self.epochs):
             self.MFbase.train()
@@ -286,19 +301,12 @@ class SPMF(object):
                 self._step(T(bat_user), T(bat_item), T(bat_neg), self.lambda_u, self.lambda_i)
             loss_all = self._loss[1].item() / max(itr, 1)
             print("epoch: {} ,time:{:.1f}, loss:{:.4f}".format(epoch, time.time() - s_time, loss_all))
-            if epoch % 1 == 0:
-                not_chang += 1
-                F_recall, F_ndcg, _, _ = self.test(now_test)
-                print("        epoch test---", "recall(5,10,20):", F_recall, "ndcg (5,10,20):", F_ndcg)
-                if max_recall20 < F_recall[-1]:
-                    max_recall20 = F_recall[-1]
-                    max_recall = F_recall
-                    max_Ndcg = F_ndcg
-                    not_chang = 0
-                if not_chang >= 5:
-                    if self.pool_init_type == 1:
-                        break
-        del max_recall, max_Ndcg
+            best.stale += 1                                   # tested after every epoch (:287)
+            F_recall, F_ndcg, _, _ = self.test(now_test)
+            print("        epoch test---", "recall(5,10,20):", F_recall, "ndcg (5,10,20):", F_ndcg)
+            best.update(F_recall, F_ndcg)
+            if best.stale >= 5 and self.pool_init_type == 1:
+                break
         self.updata_reservious(set_t)
         F_recall, F_ndcg, hit_new_user, hit_new_item = self.test(now_test)
         print("FInal test---", "recall(5,10,20):", F_recall, "ndcg (5,10,20):", F_ndcg, "hit new user:", hit_new_user, "hit new item:", hit_new_item)
@@ -308,25 +316,17 @@ class SPMF(object):
 
     def run_one_stage2(self, stage_id, read_data_type="only_new"):
         """Full-retrain ("not_only_new") and fine-tune ("only_new"), one period (reference: model/baseline.py:306-386)."""
-        set_t, now_test = self.get_next_data(stage_id, types=read_data_type)
-        if set_t is None:
+        begun = self._begin_stage(stage_id, read_data_type)
+        if begun is None:
             return False
-        self.test_num.append(now_test.shape[0])
-        self.all_item = np.union1d(self.all_item, set_t[:, 1])
+        _, now_test, train_data = begun
         if self.Reservious.pool_have > 0:
-            train_data = np.concatenate([self.Reservious.pool[0:self.Reservious.pool_have], set_t], axis=0)
             print("pool having.....")
-        else:
-            train_data = set_t
-        self.user_hit_num_in_W_R(train_data)
         train = offlineDataset_withsample(train_data)
         print("start train...")
         F_recall, F_ndcg, _, _ = self.test(now_test)
         print("before train test---", "recall(5,10,20):", F_recall, "ndcg (5,10,20):", F_ndcg)
-        max_recall20 = 0
-        max_recall = None
-        max_Ndcg = None
-        not_chang = 0
+        best = self._Best()
         self.stage_losses = []
         for epoch in range(self.epochs):
             self.MFbase.train()
@@ -335,20 +335,15 @@ class SPMF(object):
             loss_all = loss_sum / nb                                           # / (bat_num+1) (:362)
             self.stage_losses.append(loss_all)
             print("epoch: {} ,time:{:.1f}, loss:{:.4f}".format(epoch, time.time() - s_time, loss_all))
-            not_chang += 1
-            if epoch % 5 == 0:
+            best.stale += 1
+            if epoch % 5 == 0:                                # tested every fifth epoch (:365)
                 F_recall, F_ndcg, _, _ = self.test(now_test)
                 print("        epoch test---", "recall(5,10,20):", F_recall, "ndcg (5,10,20):", F_ndcg)
-                if max_recall20 < F_recall[-1]:
-                    max_recall20 = F_recall[-1]
-                    max_recall = F_recall
-                    max_Ndcg = F_ndcg
-                    not_chang = 0
-                if not_chang > 5:
-                    if self.pool_init_type == 1:
-                        break
+                best.update(F_recall, F_ndcg)
+                if best.stale > 5 and self.pool_init_type == 1:
+                    break
         F_recall, F_ndcg, hit_newu, hit_newi = self.test(now_test, stage_idx=stage_id)
-        print("max result ", max_recall, max_Ndcg)
+        print("max result ", best.recall, best.ndcg)
         print("FInal test---", "recall(5,10,20):", F_recall, "ndcg (5,10,20):", F_ndcg, "hit user:", hit_newu, "hit item:", hit_newi)
         self.recall.append(F_recall)
         self.ndcg.append(F_ndcg)
@@ -424,49 +419,40 @@ class SPMF(object):
         return bat_user.reshape(-1, 1), bat_item.reshape(-1, 1), bat_neg
 
     def run(self, start_stage, method="full"):
-        """reference: model/baseline.py:505-556, including the weighted summaries."""
+        """reference: model/baseline.py:505-556: periods until the stream ends, then the weighted summaries (first third of
+        the test periods = validation, the rest = test, all periods)."""
         self.run_stage = 0
         stage_id = start_stage
         self.summary = {}
-        while 1:
+        step = {"spmf": self.run_one_stage,
+                "full": lambda sid: self.run_one_stage2(sid, read_data_type="not_only_new")}.get(
+                    method, lambda sid: self.run_one_stage2(sid, read_data_type="only_new"))
+        while True:
             print("#################################runing stage:{}########################".format(stage_id))
-            if method == "spmf":
-                run_flag = self.run_one_stage(stage_id)
-            elif method == "full":
-                run_flag = self.run_one_stage2(stage_id, read_data_type="not_only_new")
-            else:
-                run_flag = self.run_one_stage2(stage_id, read_data_type="only_new")
-            if run_flag:
-                stage_id += 1
-                self.run_stage += 1
-            else:
-                test_num = np.array(self.test_num).reshape(-1, 1)
-                recall = np.array(self.recall)
-                ndcg = np.array(self.ndcg)
-                print("average recall:", recall.mean(axis=0))
-                print("average recall:", ndcg.mean(axis=0))       # sic (:521)
-                print(test_num)
-                print(recall)
-                print(ndcg)
-                print("hit new user:", self.hit_new_user)
-                print("hit new item:", self.hit_new_item)
-                N = test_num.shape[0]
-                N3 = round(N * 1.0 / 3)
-                pre3_num = test_num[0:N3]
-                rate3 = pre3_num / pre3_num.sum()
-                recall3 = recall[0:N3] * rate3
-                ndcg3 = ndcg[0:N3] * rate3
-                print("pre 3 (val) reslut,recall,ndcg:", recall3.sum(axis=0), ndcg3.sum(axis=0))
-                rate_7 = test_num[N3:] / test_num[N3:].sum()
-                recall7 = recall[N3:] * rate_7
-                ndcg7 = ndcg[N3:] * rate_7
-                print("last 7 (test) results,recall ,ndcg:", recall7.sum(axis=0), ndcg7.sum(axis=0))
-                rate = test_num / test_num.sum()
-                self.summary = dict(val_recall=recall3.sum(axis=0), val_ndcg=ndcg3.sum(axis=0), test_recall=recall7.sum(axis=0),
-                                    test_ndcg=ndcg7.sum(axis=0), recall=(recall * rate).sum(axis=0), ndcg=(ndcg * rate).sum(axis=0))
-                print("weight average recall@20:", self.summary["recall"])
-                print("weight average ndcg@20:", self.summary["ndcg"])
+            if not step(stage_id):
                 break
+            stage_id += 1
+            self.run_stage += 1
+        test_num = np.array(self.test_num).reshape(-1, 1)
+        recall, ndcg = np.array(self.recall), np.array(self.ndcg)
+        print("average recall:", recall.mean(axis=0))
+        print("average recall:", ndcg.mean(axis=0))               # sic (:521)
+        print(test_num)
+        print(recall)
+        print(ndcg)
+        print("hit new user:", self.hit_new_user)
+        print("hit new item:", self.hit_new_item)
+        N3 = round(test_num.shape[0] * 1.0 / 3)
+
+        def weighted(lo, hi):
+            w = test_num[lo:hi] / test_num[lo:hi].sum()
+            return (recall[lo:hi] * w).sum(axis=0), (ndcg[lo:hi] * w).sum(axis=0)
+        val, tst, both = weighted(0, N3), weighted(N3, None), weighted(0, None)
+        print("pre 3 (val) reslut,recall,ndcg:", val[0], val[1])
+        print("last 7 (test) results,recall ,ndcg:", tst[0], tst[1])
+        self.summary = dict(val_recall=val[0], val_ndcg=val[1], test_recall=tst[0], test_ndcg=tst[1], recall=both[0], ndcg=both[1])
+        print("weight average recall@20:", both[0])
+        print("weight average ndcg@20:", both[1])
 
 
 class StreamingData(object):
